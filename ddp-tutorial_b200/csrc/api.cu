@@ -1,0 +1,170 @@
+// extern "C" surface of libb2ddp.so -- see include/b2ddp.h for the contract and the
+// reference line each entry replaces.  Nothing throws across this boundary.
+#include <stdarg.h>
+#include <new>
+
+#include "model.cuh"
+
+namespace b2 {
+thread_local char g_err[1024] = {0};
+int64_t g_launches = 0;
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace b2
+
+using namespace b2;
+
+struct b2_model { Model *m; };
+
+#define GUARD_BEGIN try {
+#define GUARD_END                                                       \
+    } catch (const std::bad_alloc &) {                                  \
+        set_error("out of host memory"); return B2_ERR_STATE;           \
+    } catch (...) {                                                     \
+        set_error("unexpected C++ exception"); return B2_ERR_STATE;     \
+    }
+
+extern "C" {
+
+int b2_version(void) { return 100; }
+const char *b2_last_error(void) { return g_err; }
+int64_t b2_launch_count(void) { return g_launches; }
+
+int b2_model_create(int kind, int batch, int num_classes, int precision, int device, b2_model **out) {
+    GUARD_BEGIN
+    B2_CHECK(out, B2_ERR_ARG, "b2_model_create: out is NULL");
+    Model *m = nullptr;
+    B2_TRY(Model::create(kind, batch, num_classes, precision, device, &m));
+    *out = new b2_model{m};
+    return 0;
+    GUARD_END
+}
+int b2_model_destroy(b2_model *h) {
+    if (!h) return 0;
+    delete h->m;
+    delete h;
+    return 0;
+}
+int64_t b2_model_param_count(const b2_model *h) { return h ? h->m->n_params : 0; }
+int b2_model_num_tensors(const b2_model *h) { return h ? (int)h->m->params.size() : 0; }
+int b2_model_tensor_info(const b2_model *h, int i, const char **name, int64_t *offset, int *rank, int64_t shape[4],
+                         int64_t stride[4]) {
+    B2_CHECK(h && i >= 0 && i < (int)h->m->params.size(), B2_ERR_ARG, "tensor_info: index %d out of range", i);
+    const ParamInfo &p = h->m->params[i];
+    if (name) *name = p.name.c_str();
+    if (offset) *offset = p.offset;
+    if (rank) *rank = p.rank;
+    for (int k = 0; k < 4; ++k) { if (shape) shape[k] = p.shape[k]; if (stride) stride[k] = p.stride[k]; }
+    return 0;
+}
+int64_t b2_model_buffer_count(const b2_model *h) { return h ? h->m->n_buffers : 0; }
+int b2_model_num_buffers(const b2_model *h) { return h ? (int)h->m->buffers.size() : 0; }
+int b2_model_buffer_info(const b2_model *h, int i, const char **name, int64_t *offset, int64_t *numel) {
+    B2_CHECK(h && i >= 0 && i < (int)h->m->buffers.size(), B2_ERR_ARG, "buffer_info: index %d out of range", i);
+    const BufferInfo &b = h->m->buffers[i];
+    if (name) *name = b.name.c_str();
+    if (offset) *offset = b.offset;
+    if (numel) *numel = b.numel;
+    return 0;
+}
+int64_t b2_model_steps_tracked(const b2_model *h) { return h ? h->m->steps_tracked : 0; }
+int b2_model_bind(b2_model *h, float *params, float *grads, float *buffers) {
+    B2_CHECK(h && params && grads, B2_ERR_ARG, "b2_model_bind: NULL argument");
+    B2_CHECK(((uintptr_t)params % 16) == 0 && ((uintptr_t)grads % 16) == 0, B2_ERR_ARG, "b2_model_bind: vectors must be 16-byte aligned");
+    h->m->p_params = params; h->m->p_grads = grads; h->m->p_buffers = buffers;
+    h->m->weights_dirty = true;
+    return 0;
+}
+int b2_model_sync_weights(b2_model *h, void *stream) {
+    GUARD_BEGIN
+    B2_CHECK(h, B2_ERR_ARG, "b2_model_sync_weights: NULL model");
+    return h->m->sync_weights((cudaStream_t)stream);
+    GUARD_END
+}
+int b2_forward(b2_model *h, const float *x, float *logits, void *stream) {
+    GUARD_BEGIN
+    B2_CHECK(h && x, B2_ERR_ARG, "b2_forward: NULL argument");
+    return h->m->forward(x, logits, (cudaStream_t)stream);
+    GUARD_END
+}
+int b2_backward(b2_model *h, const float *dlogits, void *stream) {
+    GUARD_BEGIN
+    B2_CHECK(h && dlogits, B2_ERR_ARG, "b2_backward: NULL argument");
+    return h->m->backward(dlogits, (cudaStream_t)stream);
+    GUARD_END
+}
+int b2_model_mark_weights_dirty(b2_model *h) {
+    B2_CHECK(h, B2_ERR_ARG, "NULL model");
+    h->m->weights_dirty = true;
+    return 0;
+}
+int b2_model_num_ops(const b2_model *h) { return h ? (int)h->m->ops.size() : 0; }
+int b2_model_read_activation(b2_model *h, int op, int want_grad, float *out, int64_t capacity, int64_t *numel,
+                             int shape[4], void *stream) {
+    GUARD_BEGIN
+    B2_CHECK(h && op >= 0 && op < (int)h->m->ops.size(), B2_ERR_ARG, "read_activation: op %d out of range", op);
+    const Op &o = h->m->ops[op];
+    const Tensor &t = h->m->tensors[o.out];
+    if (numel) *numel = t.numel;
+    if (shape) { shape[0] = t.N; shape[1] = t.C; shape[2] = t.H; shape[3] = t.W; }
+    if (!out) return 0;
+    B2_CHECK(capacity >= t.numel, B2_ERR_ARG, "read_activation: capacity %lld < %lld", (long long)capacity, (long long)t.numel);
+    const void *src = want_grad ? t.grad : t.val;
+    if (o.type == OP_MAXPOOL && o.out_nchw) {   // already NCHW-flat
+        B2_CHECK(t.dt == DT_F32, B2_ERR_UNSUPPORTED, "read_activation: flat bf16 tensor");
+        B2_CUDA(cudaMemcpyAsync(out, src, t.numel * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return 0;
+    }
+    return op_nhwc_to_nchw_f32(src, t.dt, out, t.N, t.C, t.H, t.W, (cudaStream_t)stream);
+    GUARD_END
+}
+
+int b2_ce_loss_grad(const float *logits, const int64_t *labels, int batch, int classes, float *loss_out, float *dlogits,
+                    void *stream) {
+    GUARD_BEGIN
+    B2_CHECK(logits && labels && loss_out, B2_ERR_ARG, "b2_ce_loss_grad: NULL argument");
+    return op_ce_loss_grad(logits, labels, batch, classes, loss_out, dlogits, (cudaStream_t)stream);
+    GUARD_END
+}
+
+int b2_sgd(float *p, const float *g, float *m, int64_t n, float lr, float momentum, float grad_scale, int first_step,
+           void *stream) {
+    GUARD_BEGIN
+    B2_CHECK(n >= 0, B2_ERR_ARG, "b2_sgd: negative length");
+    if (n == 0) return 0;
+    B2_CHECK(p && g && m, B2_ERR_ARG, "b2_sgd: NULL argument");
+    return op_sgd(p, g, m, n, lr, momentum, grad_scale, first_step, (cudaStream_t)stream);
+    GUARD_END
+}
+
+// ---- CUDA graphs -------------------------------------------------------------------
+int b2_graph_begin(void *stream) {
+    B2_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+    return 0;
+}
+int b2_graph_end(void *stream, void **graph_exec) {
+    B2_CHECK(graph_exec, B2_ERR_ARG, "b2_graph_end: NULL out");
+    cudaGraph_t g = nullptr;
+    B2_CUDA(cudaStreamEndCapture((cudaStream_t)stream, &g));
+    cudaGraphExec_t e = nullptr;
+    cudaError_t r = cudaGraphInstantiate(&e, g, 0);
+    cudaGraphDestroy(g);
+    if (r != cudaSuccess) { set_error("cudaGraphInstantiate: %s", cudaGetErrorString(r)); return B2_ERR_CUDA; }
+    *graph_exec = (void *)e;
+    return 0;
+}
+int b2_graph_launch(void *graph_exec, void *stream) {
+    B2_CHECK(graph_exec, B2_ERR_ARG, "b2_graph_launch: NULL graph");
+    B2_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream));
+    return 0;
+}
+int b2_graph_destroy(void *graph_exec) {
+    if (graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)graph_exec);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,337 @@
+// Peer-memory communicator: the DDP gradient exchange without NCCL.
+//
+// Replaces, for /root/reference/cifar_example_ddp.py:
+//   :57-58  init_process_group('nccl') + barrier()         -> IPC peer mapping + flag barrier
+//   :83,106 c10d::Reducer bucket all-reduce (reducer.hpp:524, div_factor_ :497-500)
+//   :107    optimizer.step() (sgd.py)                        -> fused into the same kernel
+//
+// Every rank maps every peer's gradient / parameter / flag buffers (cudaIpc over NVLink 5 /
+// NVSwitch: uniform bandwidth to every peer).  One kernel per bucket does
+//   one-shot : every rank reads all W gradient copies, sums them in rank order, applies SGD
+//              locally (small buckets: one NVLink round trip, one barrier pair)
+//   two-shot : rank r reduces slice r from all W peers (reduce-scatter), applies the
+//              SGD-momentum update to its slice, then stores the updated *parameters* of the
+//              slice into all W replicas (all-gather of params, not grads)
+// so neither a separate all-reduce nor a separate elementwise optimizer kernel exists.
+// Summation order is fixed (rank 0..W-1) => replicas stay bit-identical.
+#include <string.h>
+#include <vector>
+
+#include "ops.cuh"
+
+namespace b2 {
+
+constexpr int kMaxWorld = 8;
+constexpr int kCommBlocks = 64;       // blocks per comm kernel (all co-resident; same on every rank)
+constexpr int kCommThreads = 512;
+// flag layout (uint32 words): [phase 0/1][src rank][block]
+constexpr int kFlagStride = kCommBlocks;
+
+struct CommPtrs {
+    float *grads[kMaxWorld];
+    float *params[kMaxWorld];
+    uint32_t *flags[kMaxWorld];
+};
+
+struct CommState {
+    bool inited = false;
+    int rank = 0, world = 1, device = 0;
+    bool registered = false;
+    CommPtrs ptrs{};
+    int64_t n_elems = 0;
+    uint32_t *epoch = nullptr;     // local device memory: per-block barrier epoch [2][kCommBlocks]
+    int *err = nullptr;            // local device word: set by a kernel whose flag wait timed out
+    std::vector<void *> allocs;
+};
+static CommState g_comm;
+
+// ---- system-scope flag primitives ------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float *p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_peer_f4(float *p, float4 v) {
+    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// All W ranks launch the same grid; block b of every rank meets block b of every other rank.
+// phase selects one of two flag banks so that back-to-back barriers never alias.
+template <int W>
+__device__ __forceinline__ void peer_barrier(const CommPtrs &P, int rank, uint32_t *epoch_mem, int phase, int *err) {
+    __syncthreads();
+    __shared__ uint32_t s_epoch;
+    if (threadIdx.x == 0) {
+        uint32_t e = epoch_mem[phase * kCommBlocks + blockIdx.x] + 1;
+        epoch_mem[phase * kCommBlocks + blockIdx.x] = e;
+        s_epoch = e;
+    }
+    __threadfence_system();      // publish this thread's earlier stores (incl. to peers)
+    __syncthreads();
+    const uint32_t e = s_epoch;
+    if (threadIdx.x < W) {
+        const int peer = threadIdx.x;
+        uint32_t *remote = P.flags[peer] + ((phase * kMaxWorld + rank) * kFlagStride + blockIdx.x);
+        st_release_sys(remote, e);
+        const uint32_t *mine = P.flags[rank] + ((phase * kMaxWorld + peer) * kFlagStride + blockIdx.x);
+        long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
+            if (clock64() - t0 > 40000000000LL) { *err = 1; break; }   // ~20 s: fail, do not hang
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+
+__device__ __forceinline__ void sgd_apply(float4 &p, float4 &m, const float4 g, float lr, float mom, int first) {
+    if (first) m = g;
+    else {
+        m.x = __fadd_rn(__fmul_rn(m.x, mom), g.x); m.y = __fadd_rn(__fmul_rn(m.y, mom), g.y);
+        m.z = __fadd_rn(__fmul_rn(m.z, mom), g.z); m.w = __fadd_rn(__fmul_rn(m.w, mom), g.w);
+    }
+    p.x = fmaf(-lr, m.x, p.x); p.y = fmaf(-lr, m.y, p.y); p.z = fmaf(-lr, m.z, p.z); p.w = fmaf(-lr, m.w, p.w);
+}
+
+// MODE 0: plain all-reduce (result * scale written to every rank's grad buffer)
+// MODE 1: fused all-reduce/W + SGD-momentum (params updated on every rank)
+template <int W, int MODE, bool ONESHOT>
+__global__ void __launch_bounds__(kCommThreads)
+k_allreduce(const CommPtrs P, int rank, float *__restrict__ mom_buf, int64_t off, int64_t n4 /* float4 count */,
+            float scale, float lr, float momentum, int first, uint32_t *epoch_mem, int *err) {
+    peer_barrier<W>(P, rank, epoch_mem, 0, err);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ONESHOT) {
+        if (MODE == 1) {
+            for (int64_t i = tid; i < n4; i += stride) {
+                const int64_t e = off + i * 4;
+                float4 acc = ld_peer_f4(P.grads[0] + e);
+#pragma unroll
+                for (int r = 1; r < W; ++r) acc = f4_add(acc, ld_peer_f4(P.grads[r] + e));
+                acc = f4_scale(acc, scale);
+                float4 p = *(float4 *)(P.params[rank] + e), m = first ? acc : *(float4 *)(mom_buf + e);
+                sgd_apply(p, m, acc, lr, momentum, first);
+                *(float4 *)(mom_buf + e) = m;
+                *(float4 *)(P.params[rank] + e) = p;
+            }
+            peer_barrier<W>(P, rank, epoch_mem, 1, err);      // peers are done reading my grads
+        } else {
+            // at most one float4 per thread (host guarantees n4 <= grid*block): read all, barrier, write own
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int64_t e = off + tid * 4;
+            if (tid < n4) {
+                acc = ld_peer_f4(P.grads[0] + e);
+#pragma unroll
+                for (int r = 1; r < W; ++r) acc = f4_add(acc, ld_peer_f4(P.grads[r] + e));
+                acc = f4_scale(acc, scale);
+            }
+            peer_barrier<W>(P, rank, epoch_mem, 1, err);
+            if (tid < n4) *(float4 *)(P.grads[rank] + e) = acc;
+        }
+    } else {
+        // slice owned by this rank, in float4 units
+        const int64_t per = (n4 + W - 1) / W;
+        const int64_t lo = (int64_t)rank * per;
+        int64_t hi = lo + per; if (hi > n4) hi = n4;
+        for (int64_t i = lo + tid; i < hi; i += stride) {
+            const int64_t e = off + i * 4;
+            float4 acc = ld_peer_f4(P.grads[0] + e);
+#pragma unroll
+            for (int r = 1; r < W; ++r) acc = f4_add(acc, ld_peer_f4(P.grads[r] + e));
+            acc = f4_scale(acc, scale);
+            if (MODE == 1) {
+                float4 p = *(float4 *)(P.params[rank] + e), m = first ? acc : *(float4 *)(mom_buf + e);
+                sgd_apply(p, m, acc, lr, momentum, first);
+                *(float4 *)(mom_buf + e) = m;
+#pragma unroll
+                for (int r = 0; r < W; ++r) st_peer_f4(P.params[r] + e, p);
+            } else {
+#pragma unroll
+                for (int r = 0; r < W; ++r) st_peer_f4(P.grads[r] + e, acc);
+            }
+        }
+        peer_barrier<W>(P, rank, epoch_mem, 1, err);          // all slices have landed everywhere
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kCommThreads)
+k_barrier_only(const CommPtrs P, int rank, uint32_t *epoch_mem, int *err) {
+    peer_barrier<W>(P, rank, epoch_mem, 0, err);
+    peer_barrier<W>(P, rank, epoch_mem, 1, err);
+}
+
+template <int MODE>
+static int launch_allreduce(int64_t off, int64_t n, float *m, float scale, float lr, float momentum, int first,
+                            int algo, cudaStream_t s) {
+    CommState &c = g_comm;
+    B2_CHECK(c.inited && c.registered, B2_ERR_STATE, "comm: not initialised / no buffers registered");
+    B2_CHECK(off >= 0 && n >= 0 && off + n <= c.n_elems, B2_ERR_ARG, "comm: range [%lld,+%lld) outside registered %lld",
+             (long long)off, (long long)n, (long long)c.n_elems);
+    B2_CHECK(off % 4 == 0, B2_ERR_ARG, "comm: offset must be a multiple of 4 elements");
+    if (n == 0) return 0;
+    const int64_t n4 = (n + 3) / 4;            // buffers are padded to 4 elements by the allocator
+    B2_CHECK(off + n4 * 4 <= (c.n_elems + 3) / 4 * 4, B2_ERR_ARG, "comm: padded range exceeds buffer");
+    const int64_t cap = (int64_t)kCommBlocks * kCommThreads;
+    bool oneshot;
+    if (algo == 1) oneshot = true;
+    else if (algo == 2) oneshot = false;
+    else oneshot = (n * 4 <= 512 * 1024);
+    if (MODE == 0 && oneshot && n4 > cap) oneshot = false;
+    if (c.world == 1) oneshot = true;
+#define LAUNCH_W(Wv)                                                                                              \
+    if (oneshot) { B2_LAUNCH((k_allreduce<Wv, MODE, true>), kCommBlocks, kCommThreads, 0, s, c.ptrs, c.rank, m, off, n4, \
+                             scale, lr, momentum, first, c.epoch, c.err); }                                           \
+    else { B2_LAUNCH((k_allreduce<Wv, MODE, false>), kCommBlocks, kCommThreads, 0, s, c.ptrs, c.rank, m, off, n4, scale,   \
+                     lr, momentum, first, c.epoch, c.err); }
+    switch (c.world) {
+    case 1: LAUNCH_W(1); break;
+    case 2: LAUNCH_W(2); break;
+    case 4: LAUNCH_W(4); break;
+    case 8: LAUNCH_W(8); break;
+    default: set_error("comm: world size %d not supported (1,2,4,8)", c.world); return B2_ERR_UNSUPPORTED;
+    }
+#undef LAUNCH_W
+    return 0;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" {
+
+int b2_comm_init(int rank, int world, int device) {
+    CommState &c = g_comm;
+    B2_CHECK(!c.inited, B2_ERR_STATE, "comm: already initialised");
+    B2_CHECK(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, B2_ERR_ARG, "comm: bad rank %d / world %d", rank, world);
+    B2_CUDA(cudaSetDevice(device));
+    c.rank = rank; c.world = world; c.device = device;
+    B2_CUDA(cudaMalloc(&c.epoch, 2 * kCommBlocks * sizeof(uint32_t)));
+    B2_CUDA(cudaMemset(c.epoch, 0, 2 * kCommBlocks * sizeof(uint32_t)));
+    B2_CUDA(cudaMalloc(&c.err, sizeof(int)));
+    B2_CUDA(cudaMemset(c.err, 0, sizeof(int)));
+    c.inited = true;
+    return 0;
+}
+
+int b2_comm_finalize(void) {
+    CommState &c = g_comm;
+    if (!c.inited) return 0;
+    cudaDeviceSynchronize();
+    for (void *p : c.allocs) cudaFree(p);
+    c.allocs.clear();
+    if (c.epoch) cudaFree(c.epoch);
+    if (c.err) cudaFree(c.err);
+    c = CommState();
+    return 0;
+}
+
+int b2_comm_alloc(int64_t bytes, void **ptr) {
+    B2_CHECK(ptr && bytes > 0, B2_ERR_ARG, "comm_alloc: bad arguments");
+    bytes = (bytes + 255) / 256 * 256;
+    void *p = nullptr;
+    B2_CUDA(cudaMalloc(&p, bytes));
+    B2_CUDA(cudaMemset(p, 0, bytes));
+    B2_CUDA(cudaDeviceSynchronize());
+    g_comm.allocs.push_back(p);
+    *ptr = p;
+    return 0;
+}
+int b2_comm_free(void *ptr) {
+    CommState &c = g_comm;
+    for (size_t i = 0; i < c.allocs.size(); ++i)
+        if (c.allocs[i] == ptr) { cudaFree(ptr); c.allocs.erase(c.allocs.begin() + i); return 0; }
+    set_error("comm_free: pointer not owned by the library");
+    return B2_ERR_ARG;
+}
+int b2_comm_export(void *ptr, void *handle_out) {
+    B2_CHECK(ptr && handle_out, B2_ERR_ARG, "comm_export: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == B2_IPC_HANDLE_BYTES, "ipc handle size");
+    cudaIpcMemHandle_t h;
+    B2_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+int b2_comm_import(const void *handle, void **peer_ptr) {
+    B2_CHECK(handle && peer_ptr, B2_ERR_ARG, "comm_import: NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    B2_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int b2_comm_unimport(void *peer_ptr) {
+    if (peer_ptr) B2_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return 0;
+}
+
+int b2_comm_register(void *const *grads, void *const *params, void *const *flags, int64_t n_elems) {
+    CommState &c = g_comm;
+    B2_CHECK(c.inited, B2_ERR_STATE, "comm: not initialised");
+    B2_CHECK(grads && flags && n_elems > 0, B2_ERR_ARG, "comm_register: bad arguments");
+    for (int r = 0; r < c.world; ++r) {
+        B2_CHECK(grads[r] && flags[r], B2_ERR_ARG, "comm_register: NULL buffer for rank %d", r);
+        c.ptrs.grads[r] = (float *)grads[r];
+        c.ptrs.params[r] = params ? (float *)params[r] : nullptr;
+        c.ptrs.flags[r] = (uint32_t *)flags[r];
+    }
+    c.n_elems = n_elems;
+    c.registered = true;
+    return 0;
+}
+
+int b2_comm_flag_bytes(void) { return 2 * kMaxWorld * kFlagStride * (int)sizeof(uint32_t); }
+
+int b2_comm_check(void) {
+    // host-side: did any comm kernel time out on a flag wait?  (synchronises the device)
+    CommState &c = g_comm;
+    B2_CHECK(c.inited, B2_ERR_STATE, "comm: not initialised");
+    int e = 0;
+    B2_CUDA(cudaMemcpy(&e, c.err, sizeof(int), cudaMemcpyDeviceToHost));
+    B2_CHECK(e == 0, B2_ERR_TIMEOUT, "comm: a peer flag wait timed out (a rank died or diverged)");
+    return 0;
+}
+
+int b2_comm_barrier(void *stream) {
+    CommState &c = g_comm;
+    B2_CHECK(c.inited && c.registered, B2_ERR_STATE, "comm: not initialised / no buffers registered");
+    switch (c.world) {
+    case 1: return 0;
+    case 2: B2_LAUNCH((k_barrier_only<2>), kCommBlocks, kCommThreads, 0, stream, c.ptrs, c.rank, c.epoch, c.err); break;
+    case 4: B2_LAUNCH((k_barrier_only<4>), kCommBlocks, kCommThreads, 0, stream, c.ptrs, c.rank, c.epoch, c.err); break;
+    case 8: B2_LAUNCH((k_barrier_only<8>), kCommBlocks, kCommThreads, 0, stream, c.ptrs, c.rank, c.epoch, c.err); break;
+    default: set_error("comm: world size %d not supported", c.world); return B2_ERR_UNSUPPORTED;
+    }
+    return 0;
+}
+
+int b2_allreduce(int64_t n_elems, float scale, int algo, void *stream) {
+    return launch_allreduce<0>(0, n_elems, nullptr, scale, 0.f, 0.f, 0, algo, (cudaStream_t)stream);
+}
+int b2_allreduce_range(int64_t offset, int64_t n_elems, float scale, int algo, void *stream) {
+    return launch_allreduce<0>(offset, n_elems, nullptr, scale, 0.f, 0.f, 0, algo, (cudaStream_t)stream);
+}
+
+int b2_allreduce_sgd(float *m, int64_t n_elems, float lr, float momentum, int first_step, int algo, void *stream) {
+    B2_CHECK(m, B2_ERR_ARG, "allreduce_sgd: NULL momentum buffer");
+    B2_CHECK(g_comm.ptrs.params[0] != nullptr, B2_ERR_STATE, "allreduce_sgd: no parameter buffers registered");
+    return launch_allreduce<1>(0, n_elems, m, 1.f / (float)g_comm.world, lr, momentum, first_step, algo, (cudaStream_t)stream);
+}
+int b2_allreduce_sgd_range(float *m, int64_t offset, int64_t n_elems, float lr, float momentum, int first_step, int algo,
+                           void *stream) {
+    B2_CHECK(m, B2_ERR_ARG, "allreduce_sgd: NULL momentum buffer");
+    B2_CHECK(g_comm.ptrs.params[0] != nullptr, B2_ERR_STATE, "allreduce_sgd: no parameter buffers registered");
+    return launch_allreduce<1>(offset, n_elems, m, 1.f / (float)g_comm.world, lr, momentum, first_step, algo, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,386 @@
+// Static-graph executor for the three topologies on the reference's hot path:
+//   Net          /root/reference/cifar_example_ddp.py:23-40
+//   ResNet-18/50 torchvision/models/resnet.py:166-285 (substituted at cifar_example.py:60)
+// forward = net(inputs) (cifar_example_ddp.py:104), backward = loss.backward() (:106).
+// There is no autograd: the backward schedule is fixed when the model is built, every
+// gradient lands in the caller's flat fp32 grad vector (the DDP bucket, reducer.hpp:347).
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include <string>
+#include <algorithm>
+
+#include "model.cuh"
+
+namespace b2 {
+
+// =================================================================================
+// graph construction
+// =================================================================================
+int Model::add_tensor(int N, int H, int W, int C, int dt) {
+    Tensor t{};
+    t.N = N; t.H = H; t.W = W; t.C = C; t.dt = dt;
+    tensors.push_back(t);
+    return (int)tensors.size() - 1;
+}
+
+int64_t Model::add_param(const std::string &name, int rank, const int64_t *shape, const int64_t *stride, int64_t numel) {
+    ParamInfo p{};
+    p.name = name; p.rank = rank; p.numel = numel;
+    for (int i = 0; i < 4; ++i) { p.shape[i] = i < rank ? shape[i] : 1; p.stride[i] = i < rank ? stride[i] : 0; }
+    p.offset = n_params;
+    n_params += (numel + 3) / 4 * 4;     // keep every tensor 16-byte aligned in the flat vector
+    params.push_back(p);
+    return p.offset;
+}
+int64_t Model::add_buffer(const std::string &name, int64_t numel) {
+    BufferInfo b{};
+    b.name = name; b.numel = numel; b.offset = n_buffers;
+    n_buffers += (numel + 3) / 4 * 4;
+    buffers.push_back(b);
+    return b.offset;
+}
+
+// conv weight stored O,H,W,I; torch's logical O,I,H,W shape is a strided view of it
+int64_t Model::add_conv_weight(const std::string &name, int Co, int Ci, int kh, int kw) {
+    int64_t shape[4] = {Co, Ci, kh, kw};
+    int64_t stride[4] = {(int64_t)kh * kw * Ci, 1, (int64_t)kw * Ci, Ci};
+    return add_param(name, 4, shape, stride, (int64_t)Co * Ci * kh * kw);
+}
+int64_t Model::add_vec(const std::string &name, int n) {
+    int64_t shape[1] = {n}, stride[1] = {1};
+    return add_param(name, 1, shape, stride, n);
+}
+int64_t Model::add_mat(const std::string &name, int rows, int cols) {
+    int64_t shape[2] = {rows, cols}, stride[2] = {cols, 1};
+    return add_param(name, 2, shape, stride, (int64_t)rows * cols);
+}
+
+int Model::op_conv(int in, int64_t w_off, int64_t b_off, int Co, int k, int stride, int pad, bool relu, int out_dt) {
+    const Tensor &ti = tensors[in];
+    Op o{};
+    o.type = OP_CONV; o.in = in; o.res = -1;
+    o.g.N = ti.N; o.g.Hi = ti.H; o.g.Wi = ti.W; o.g.Ci = ti.C;
+    o.g.kh = o.g.kw = k; o.g.stride = stride; o.g.pad = pad;
+    o.g.Ho = (ti.H + 2 * pad - k) / stride + 1; o.g.Wo = (ti.W + 2 * pad - k) / stride + 1; o.g.Co = Co;
+    o.w_off = w_off; o.b_off = b_off; o.relu = relu;
+    o.out = add_tensor(ti.N, o.g.Ho, o.g.Wo, Co, out_dt < 0 ? ti.dt : out_dt);
+    ops.push_back(o);
+    return o.out;
+}
+int Model::op_bn(int in, int64_t g_off, int64_t b_off, int64_t rm_off, int64_t rv_off, bool relu, int res) {
+    const Tensor &ti = tensors[in];
+    Op o{};
+    o.type = OP_BN; o.in = in; o.res = res; o.relu = relu;
+    o.w_off = g_off; o.b_off = b_off; o.rm_off = rm_off; o.rv_off = rv_off;
+    o.out = add_tensor(ti.N, ti.H, ti.W, ti.C, ti.dt);
+    ops.push_back(o);
+    return o.out;
+}
+int Model::op_maxpool(int in, int k, int stride, int pad, bool out_nchw_flat) {
+    const Tensor &ti = tensors[in];
+    Op o{};
+    o.type = OP_MAXPOOL; o.in = in; o.res = -1;
+    o.g.N = ti.N; o.g.Hi = ti.H; o.g.Wi = ti.W; o.g.Ci = ti.C; o.g.Co = ti.C;
+    o.g.kh = o.g.kw = k; o.g.stride = stride; o.g.pad = pad;
+    o.g.Ho = (ti.H + 2 * pad - k) / stride + 1; o.g.Wo = (ti.W + 2 * pad - k) / stride + 1;
+    o.out_nchw = out_nchw_flat;
+    if (out_nchw_flat) o.out = add_tensor(ti.N, 1, 1, ti.C * o.g.Ho * o.g.Wo, ti.dt);
+    else o.out = add_tensor(ti.N, o.g.Ho, o.g.Wo, ti.C, ti.dt);
+    ops.push_back(o);
+    return o.out;
+}
+int Model::op_avgpool(int in) {
+    const Tensor &ti = tensors[in];
+    Op o{};
+    o.type = OP_AVGPOOL; o.in = in; o.res = -1;
+    o.out = add_tensor(ti.N, 1, 1, ti.C, DT_F32);
+    ops.push_back(o);
+    return o.out;
+}
+
+// ---- Net (cifar_example_ddp.py:23-40): always fp32 -- its GEMMs (K=75/150, N=6/16) are far
+// below tensor-core tile sizes
+void Model::build_net() {
+    int64_t c1w = add_conv_weight("conv1.weight", 6, 3, 5, 5), c1b = add_vec("conv1.bias", 6);
+    int64_t c2w = add_conv_weight("conv2.weight", 16, 6, 5, 5), c2b = add_vec("conv2.bias", 16);
+    int64_t f1w = add_mat("fc1.weight", 120, 400), f1b = add_vec("fc1.bias", 120);
+    int64_t f2w = add_mat("fc2.weight", 84, 120), f2b = add_vec("fc2.bias", 84);
+    int64_t f3w = add_mat("fc3.weight", num_classes, 84), f3b = add_vec("fc3.bias", num_classes);
+    int x = add_tensor(batch, 32, 32, 3, DT_F32);
+    input_tensor = x;
+    Op in{}; in.type = OP_INPUT; in.in = -1; in.out = x; in.res = -1; ops.push_back(in);
+    int t = op_conv(x, c1w, c1b, 6, 5, 1, 0, true, -1);
+    t = op_maxpool(t, 2, 2, 0, false);
+    t = op_conv(t, c2w, c2b, 16, 5, 1, 0, true, -1);
+    t = op_maxpool(t, 2, 2, 0, true);                  // torch.flatten(x, 1) of NCHW: (c,h,w) order
+    t = op_conv(t, f1w, f1b, 120, 1, 1, 0, true, -1);  // Linear == 1x1 conv on [B,1,1,K]
+    t = op_conv(t, f2w, f2b, 84, 1, 1, 0, true, -1);
+    t = op_conv(t, f3w, f3b, num_classes, 1, 1, 0, false, DT_F32);
+    logits_tensor = t;
+}
+
+struct BnIds { int64_t g, b, rm, rv; };
+static BnIds add_bn_params(Model &m, const std::string &prefix, int C) {
+    BnIds r;
+    r.g = m.add_vec(prefix + ".weight", C);
+    r.b = m.add_vec(prefix + ".bias", C);
+    r.rm = m.add_buffer(prefix + ".running_mean", C);
+    r.rv = m.add_buffer(prefix + ".running_var", C);
+    return r;
+}
+
+// ---- torchvision ResNet (resnet.py:166-285); BasicBlock :59-105, Bottleneck :108-163
+void Model::build_resnet(bool bottleneck, const int layers[4]) {
+    const int adt = precision == B2_PREC_BF16 ? DT_BF16 : DT_F32;
+    int64_t c1w = add_conv_weight("conv1.weight", 64, 3, 7, 7);
+    BnIds b1 = add_bn_params(*this, "bn1", 64);
+    int x = add_tensor(batch, 32, 32, 3, adt);
+    input_tensor = x;
+    Op in{}; in.type = OP_INPUT; in.in = -1; in.out = x; in.res = -1; ops.push_back(in);
+    int t = op_conv(x, c1w, -1, 64, 7, 2, 3, false, -1);
+    t = op_bn(t, b1.g, b1.b, b1.rm, b1.rv, true, -1);
+    t = op_maxpool(t, 3, 2, 1, false);
+    int inplanes = 64;
+    const int expansion = bottleneck ? 4 : 1;
+    for (int L = 0; L < 4; ++L) {
+        int planes = 64 << L;
+        for (int bi = 0; bi < layers[L]; ++bi) {
+            int stride = (bi == 0 && L > 0) ? 2 : 1;
+            std::string pre = "layer" + std::to_string(L + 1) + "." + std::to_string(bi);
+            bool down = (stride != 1) || (inplanes != planes * expansion);
+            // parameters in torch registration order: conv1,bn1,conv2,bn2,(conv3,bn3),downsample
+            int64_t w1, w2, w3 = -1, wd = -1;
+            BnIds n1, n2, n3{}, nd{};
+            if (!bottleneck) {
+                w1 = add_conv_weight(pre + ".conv1.weight", planes, inplanes, 3, 3); n1 = add_bn_params(*this, pre + ".bn1", planes);
+                w2 = add_conv_weight(pre + ".conv2.weight", planes, planes, 3, 3);   n2 = add_bn_params(*this, pre + ".bn2", planes);
+            } else {
+                w1 = add_conv_weight(pre + ".conv1.weight", planes, inplanes, 1, 1); n1 = add_bn_params(*this, pre + ".bn1", planes);
+                w2 = add_conv_weight(pre + ".conv2.weight", planes, planes, 3, 3);   n2 = add_bn_params(*this, pre + ".bn2", planes);
+                w3 = add_conv_weight(pre + ".conv3.weight", planes * 4, planes, 1, 1); n3 = add_bn_params(*this, pre + ".bn3", planes * 4);
+            }
+            if (down) {
+                wd = add_conv_weight(pre + ".downsample.0.weight", planes * expansion, inplanes, 1, 1);
+                nd = add_bn_params(*this, pre + ".downsample.1", planes * expansion);
+            }
+            int idn = t;
+            if (down) {
+                int d = op_conv(t, wd, -1, planes * expansion, 1, stride, 0, false, -1);
+                idn = op_bn(d, nd.g, nd.b, nd.rm, nd.rv, false, -1);
+            }
+            int o;
+            if (!bottleneck) {
+                o = op_conv(t, w1, -1, planes, 3, stride, 1, false, -1);
+                o = op_bn(o, n1.g, n1.b, n1.rm, n1.rv, true, -1);
+                o = op_conv(o, w2, -1, planes, 3, 1, 1, false, -1);
+                o = op_bn(o, n2.g, n2.b, n2.rm, n2.rv, true, idn);
+            } else {
+                o = op_conv(t, w1, -1, planes, 1, 1, 0, false, -1);
+                o = op_bn(o, n1.g, n1.b, n1.rm, n1.rv, true, -1);
+                o = op_conv(o, w2, -1, planes, 3, stride, 1, false, -1);
+                o = op_bn(o, n2.g, n2.b, n2.rm, n2.rv, true, -1);
+                o = op_conv(o, w3, -1, planes * 4, 1, 1, 0, false, -1);
+                o = op_bn(o, n3.g, n3.b, n3.rm, n3.rv, true, idn);
+            }
+            t = o;
+            inplanes = planes * expansion;
+        }
+    }
+    int64_t fw = add_mat("fc.weight", num_classes, inplanes), fb = add_vec("fc.bias", num_classes);
+    t = op_avgpool(t);
+    t = op_conv(t, fw, fb, num_classes, 1, 1, 0, false, DT_F32);
+    logits_tensor = t;
+}
+
+// =================================================================================
+// finalisation: backward schedule flags, memory
+// =================================================================================
+int Model::finalize() {
+    // which gradients are first-written vs accumulated, in reverse op order
+    std::vector<int> written(tensors.size(), 0);
+    for (int i = (int)ops.size() - 1; i >= 0; --i) {
+        Op &o = ops[i];
+        if (o.type == OP_INPUT) continue;
+        o.need_dgrad = ops_produce(o.in);
+        if (o.need_dgrad) { o.acc_in = written[o.in] != 0; written[o.in] = 1; }
+        if (o.res >= 0) { o.acc_res = written[o.res] != 0; written[o.res] = 1; }
+    }
+    // ---- device memory: one slab for activations + grads + per-op scratch
+    size_t total = 0;
+    auto reserve = [&](size_t bytes) { size_t off = total; total += (bytes + 255) / 256 * 256; return off; };
+    std::vector<size_t> voff(tensors.size()), goff(tensors.size());
+    for (size_t i = 0; i < tensors.size(); ++i) {
+        Tensor &t = tensors[i];
+        t.numel = (int64_t)t.N * t.H * t.W * t.C;
+        voff[i] = reserve(t.numel * dt_size(t.dt));
+        goff[i] = reserve(t.numel * dt_size(t.dt));
+    }
+    struct Scratch { size_t partial, mean, invstd, coef, idx, wcopy; };
+    std::vector<Scratch> so(ops.size());
+    size_t wg_floats = 0;
+    for (size_t i = 0; i < ops.size(); ++i) {
+        Op &o = ops[i];
+        if (o.type == OP_BN) {
+            const Tensor &t = tensors[o.in];
+            int64_t M = (int64_t)t.N * t.H * t.W;
+            o.bn.row_blocks = bn_row_blocks(M, t.C);
+            so[i].partial = reserve((size_t)o.bn.row_blocks * 2 * t.C * 4);
+            so[i].mean = reserve(t.C * 4); so[i].invstd = reserve(t.C * 4); so[i].coef = reserve(3 * t.C * 4);
+        } else if (o.type == OP_MAXPOOL) {
+            so[i].idx = reserve((size_t)o.g.N * o.g.Ho * o.g.Wo * o.g.Ci);
+        } else if (o.type == OP_CONV) {
+            wg_floats = std::max(wg_floats, conv_simt_wgrad_workspace(o.g));
+            o.wdt = DT_F32; o.wpitch = o.g.K();
+            if (tensors[o.in].dt == DT_BF16) {
+                o.wdt = DT_BF16; o.wpitch = (o.g.K() + 63) / 64 * 64;
+                so[i].wcopy = reserve((size_t)o.g.Co * o.wpitch * 2);
+            }
+        }
+    }
+    size_t wg_off = reserve(wg_floats * 4 + 256);
+    wgrad_floats = wg_floats;
+    B2_CUDA(cudaMalloc(&slab, total));
+    B2_CUDA(cudaMemset(slab, 0, total));
+    slab_bytes = total;
+    char *base = (char *)slab;
+    for (size_t i = 0; i < tensors.size(); ++i) { tensors[i].val = base + voff[i]; tensors[i].grad = base + goff[i]; }
+    for (size_t i = 0; i < ops.size(); ++i) {
+        Op &o = ops[i];
+        if (o.type == OP_BN) {
+            o.bn.partial = (float *)(base + so[i].partial); o.bn.mean = (float *)(base + so[i].mean);
+            o.bn.invstd = (float *)(base + so[i].invstd); o.bn.coef = (float *)(base + so[i].coef);
+        } else if (o.type == OP_MAXPOOL) {
+            o.idx = (uint8_t *)(base + so[i].idx);
+        } else if (o.type == OP_CONV && o.wdt == DT_BF16) {
+            o.wcopy = (bf16 *)(base + so[i].wcopy);
+        }
+    }
+    wgrad_ws = (float *)(base + wg_off);
+    return 0;
+}
+
+bool Model::ops_produce(int tensor) const {
+    // does any differentiable op produce this tensor (i.e. is a gradient w.r.t. it needed)?
+    for (const Op &o : ops)
+        if (o.out == tensor) return o.type != OP_INPUT;
+    return false;
+}
+
+Model::~Model() {
+    if (slab) cudaFree(slab);
+}
+
+// =================================================================================
+// execution
+// =================================================================================
+int Model::sync_weights(cudaStream_t s) {
+    B2_CHECK(p_params, B2_ERR_STATE, "model: parameters not bound");
+    for (Op &o : ops)
+        if (o.type == OP_CONV && o.wdt == DT_BF16)
+            B2_TRY(op_f32_to_bf16_padded(p_params + o.w_off, o.wcopy, o.g.Co, o.g.K(), o.wpitch, s));
+    weights_dirty = false;
+    return 0;
+}
+
+int Model::forward(const float *x_nchw, float *logits, cudaStream_t s) {
+    B2_CHECK(p_params && p_grads, B2_ERR_STATE, "model: parameters/gradients not bound (b2_model_bind)");
+    if (weights_dirty) B2_TRY(sync_weights(s));
+    for (Op &o : ops) {
+        Tensor &to = tensors[o.out];
+        switch (o.type) {
+        case OP_INPUT:
+            B2_TRY(op_nchw_to_nhwc(x_nchw, to.val, to.dt, to.N, to.C, to.H, to.W, s));
+            break;
+        case OP_CONV: {
+            Tensor &ti = tensors[o.in];
+            const void *w = o.wdt == DT_BF16 ? (const void *)o.wcopy : (const void *)(p_params + o.w_off);
+            const float *bias = o.b_off >= 0 ? p_params + o.b_off : nullptr;
+            B2_TRY(conv_simt_fprop(o.g, ti.val, ti.dt, w, o.wdt, o.wpitch, bias, o.relu, to.val, to.dt, s));
+            if (o.out == logits_tensor && logits)
+                B2_CUDA(cudaMemcpyAsync(logits, to.val, to.numel * 4, cudaMemcpyDeviceToDevice, s));
+            break;
+        }
+        case OP_BN: {
+            Tensor &ti = tensors[o.in];
+            int64_t M = (int64_t)ti.N * ti.H * ti.W;
+            B2_TRY(op_bn_forward(ti.val, to.val, o.res >= 0 ? tensors[o.res].val : nullptr, ti.dt, M, ti.C,
+                                 p_params + o.w_off, p_params + o.b_off, p_buffers ? p_buffers + o.rm_off : nullptr,
+                                 p_buffers ? p_buffers + o.rv_off : nullptr, 1e-5f, 0.1f, o.relu, o.bn, s));
+            break;
+        }
+        case OP_MAXPOOL: {
+            Tensor &ti = tensors[o.in];
+            B2_TRY(op_maxpool_forward(ti.val, to.val, o.idx, ti.dt, o.g.N, o.g.Hi, o.g.Wi, o.g.Ci, o.g.kh, o.g.stride,
+                                      o.g.pad, o.g.Ho, o.g.Wo, o.out_nchw, s));
+            break;
+        }
+        case OP_AVGPOOL: {
+            Tensor &ti = tensors[o.in];
+            B2_TRY(op_avgpool_forward(ti.val, ti.dt, (float *)to.val, ti.N, ti.H * ti.W, ti.C, s));
+            break;
+        }
+        }
+    }
+    ++steps_tracked;
+    return 0;
+}
+
+int Model::backward(const float *dlogits, cudaStream_t s) {
+    B2_CHECK(p_params && p_grads, B2_ERR_STATE, "model: parameters/gradients not bound (b2_model_bind)");
+    Tensor &tl = tensors[logits_tensor];
+    B2_CUDA(cudaMemcpyAsync(tl.grad, dlogits, tl.numel * 4, cudaMemcpyDeviceToDevice, s));
+    for (int i = (int)ops.size() - 1; i >= 0; --i) {
+        Op &o = ops[i];
+        if (o.type == OP_INPUT) continue;
+        Tensor &to = tensors[o.out];
+        Tensor &ti = tensors[o.in];
+        switch (o.type) {
+        case OP_CONV: {
+            if (o.relu) B2_TRY(op_relu_mask(to.val, to.grad, to.dt, to.numel, s));
+            if (o.b_off >= 0) B2_TRY(op_bias_grad(to.grad, to.dt, o.g.M(), o.g.Co, p_grads + o.b_off, s));
+            B2_CHECK(to.dt == ti.dt, B2_ERR_STATE, "conv backward: mixed activation types");
+            B2_TRY(conv_simt_wgrad(o.g, ti.val, to.grad, ti.dt, p_grads + o.w_off, wgrad_ws, wgrad_floats, s));
+            if (o.need_dgrad) {
+                const void *w = o.wdt == DT_BF16 ? (const void *)o.wcopy : (const void *)(p_params + o.w_off);
+                B2_TRY(conv_simt_dgrad(o.g, to.grad, to.dt, w, o.wdt, o.wpitch, ti.grad, o.acc_in, s));
+            }
+            break;
+        }
+        case OP_BN: {
+            int64_t M = (int64_t)ti.N * ti.H * ti.W;
+            B2_TRY(op_bn_backward(ti.val, to.val, to.grad, ti.grad, o.res >= 0 ? tensors[o.res].grad : nullptr, ti.dt, M,
+                                  ti.C, p_params + o.w_off, p_grads + o.w_off, p_grads + o.b_off, o.relu, o.acc_in,
+                                  o.acc_res, o.bn, s));
+            break;
+        }
+        case OP_MAXPOOL:
+            if (o.need_dgrad)
+                B2_TRY(op_maxpool_backward(to.grad, o.idx, ti.grad, ti.dt, o.g.N, o.g.Hi, o.g.Wi, o.g.Ci, o.g.kh,
+                                           o.g.stride, o.g.pad, o.g.Ho, o.g.Wo, o.out_nchw, o.acc_in, s));
+            break;
+        case OP_AVGPOOL:
+            B2_TRY(op_avgpool_backward((const float *)to.grad, ti.grad, ti.dt, ti.N, ti.H * ti.W, ti.C, o.acc_in, s));
+            break;
+        }
+    }
+    return 0;
+}
+
+int Model::create(int kind, int batch, int num_classes, int precision, int device, Model **out) {
+    B2_CHECK(batch > 0 && num_classes > 0, B2_ERR_ARG, "model: batch and num_classes must be positive");
+    B2_CHECK(precision == B2_PREC_FP32 || precision == B2_PREC_BF16, B2_ERR_ARG, "model: unknown precision %d", precision);
+    B2_CUDA(cudaSetDevice(device));
+    Model *m = new Model();
+    m->kind = kind; m->batch = batch; m->num_classes = num_classes; m->precision = precision; m->device = device;
+    if (kind == B2_MODEL_NET) { m->precision = B2_PREC_FP32; m->build_net(); }
+    else if (kind == B2_MODEL_RESNET18) { const int l[4] = {2, 2, 2, 2}; m->build_resnet(false, l); }
+    else if (kind == B2_MODEL_RESNET50) { const int l[4] = {3, 4, 6, 3}; m->build_resnet(true, l); }
+    else { delete m; set_error("model: unknown kind %d", kind); return B2_ERR_ARG; }
+    int r = m->finalize();
+    if (r != 0) { delete m; return r; }
+    *out = m;
+    return 0;
+}
+
+}  // namespace b2

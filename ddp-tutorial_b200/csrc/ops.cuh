@@ -1,0 +1,70 @@
+// Launcher prototypes for the non-GEMM kernels and the SIMT (CUDA-core) conv path.
+#pragma once
+#include "common.cuh"
+
+namespace b2 {
+
+// dt: activation storage type, 0 = fp32, 1 = bf16
+enum { DT_F32 = 0, DT_BF16 = 1 };
+static inline size_t dt_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+
+// ---- layout ------------------------------------------------------------------
+int op_nchw_to_nhwc(const float *x, void *y, int dt, int N, int C, int H, int W, cudaStream_t s);
+int op_nhwc_to_nchw_f32(const void *x, int dt, float *y, int N, int C, int H, int W, cudaStream_t s);
+int op_f32_to_bf16(const float *x, bf16 *y, int64_t n, cudaStream_t s);
+// rows x k fp32 -> rows x kpad bf16 (zero padded)
+int op_f32_to_bf16_padded(const float *x, bf16 *y, int64_t rows, int k, int kpad, cudaStream_t s);
+
+// ---- batch norm (training mode, batch statistics) ---------------------------------
+struct BnWork {           // per-BN-layer scratch, all fp32 device pointers
+    float *partial;       // [bn_rows_blocks][2][C]
+    float *mean, *invstd; // [C]
+    float *coef;          // [3][C]  (a, c1, c2) for backward
+    int row_blocks;
+};
+int bn_row_blocks(int64_t M, int C);
+int op_bn_forward(const void *x, void *y, const void *res, int dt, int64_t M, int C,
+                  const float *gamma, const float *beta, float *running_mean, float *running_var,
+                  float eps, float momentum, bool relu, const BnWork &w, cudaStream_t s);
+// dy: grad wrt y (post relu/residual).  dx written (acc_dx=false) or accumulated.
+// dres (may be null): gradient of the residual input, written or accumulated.
+int op_bn_backward(const void *x, const void *y, const void *dy, void *dx, void *dres, int dt,
+                   int64_t M, int C, const float *gamma, float *dgamma, float *dbeta, bool relu,
+                   bool acc_dx, bool acc_dres, const BnWork &w, cudaStream_t s);
+
+// ---- pooling -------------------------------------------------------------------
+int op_maxpool_forward(const void *x, void *y, uint8_t *idx, int dt, int N, int Hi, int Wi, int C,
+                       int k, int stride, int pad, int Ho, int Wo, bool out_nchw, cudaStream_t s);
+int op_maxpool_backward(const void *dy, const uint8_t *idx, void *dx, int dt, int N, int Hi, int Wi,
+                        int C, int k, int stride, int pad, int Ho, int Wo, bool out_nchw, bool acc,
+                        cudaStream_t s);
+// x/dx are NHWC of type xdt; y/dy are fp32 [N][C] (the classifier head runs in fp32)
+int op_avgpool_forward(const void *x, int xdt, float *y, int N, int HW, int C, cudaStream_t s);
+int op_avgpool_backward(const float *dy, void *dx, int xdt, int N, int HW, int C, bool acc, cudaStream_t s);
+
+// ---- pointwise ------------------------------------------------------------------
+// dy = y > 0 ? dy : 0  (in place)
+int op_relu_mask(const void *y, void *dy, int dt, int64_t n, cudaStream_t s);
+// db[c] = sum_m dy[m,c]
+int op_bias_grad(const void *dy, int dt, int64_t M, int C, float *db, cudaStream_t s);
+
+// ---- SIMT implicit-GEMM convolution (fp32 FMA, any shape) ---------------------------
+// weights are O,H,W,I (K = kh*kw*Ci contiguous per output channel) with row pitch wpitch
+// elements; wdt is the weight storage type.
+int conv_simt_fprop(const ConvGeom &g, const void *x, int dt, const void *w, int wdt, int wpitch,
+                    const float *bias, bool relu, void *y, int ydt, cudaStream_t s);
+int conv_simt_dgrad(const ConvGeom &g, const void *dy, int dt, const void *w, int wdt, int wpitch,
+                    void *dx, bool acc, cudaStream_t s);
+// dw fp32 [Co][K] (pitch K); deterministic split over the pixel dimension through `partial`
+// (capacity in floats); returns the number of splits it used
+size_t conv_simt_wgrad_workspace(const ConvGeom &g);
+int conv_simt_wgrad(const ConvGeom &g, const void *x, const void *dy, int dt, float *dw,
+                    float *partial, size_t partial_floats, cudaStream_t s);
+
+// ---- loss / optimizer ------------------------------------------------------------------
+int op_ce_loss_grad(const float *logits, const int64_t *labels, int B, int C, float *loss,
+                    float *dlogits, cudaStream_t s);
+int op_sgd(float *p, const float *g, float *m, int64_t n, float lr, float momentum, float gscale,
+           int first, cudaStream_t s);
+
+}  // namespace b2

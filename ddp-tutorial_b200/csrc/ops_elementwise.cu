@@ -1,0 +1,463 @@
+// HBM-bound kernels of the training step: layout conversion, BatchNorm (train mode),
+// pooling, ReLU masks, bias gradients, cross-entropy + softmax-grad, SGD-momentum.
+//
+// Reference semantics (what torch dispatches for the cited reference lines):
+//   BatchNorm2d train fwd/bwd : torchvision resnet.py:82,198 under cifar_example.py:77-79
+//   max_pool2d                : cifar_example_ddp.py:27,34-35
+//   cross_entropy (mean)      : cifar_example_ddp.py:85,105  (functional.py:3421-3504)
+//   SGD momentum              : cifar_example_ddp.py:86,107  (sgd.py:_single_tensor_sgd)
+#include "ops.cuh"
+
+namespace b2 {
+
+#define DISPATCH_DT(dt, T, ...)                    \
+    if ((dt) == DT_F32) { typedef float T; __VA_ARGS__; } \
+    else { typedef bf16 T; __VA_ARGS__; }
+
+static inline int grid_for(int64_t n, int block, int max_blocks = kNumSMs * 16) {
+    int64_t b = ceil_div(n, block);
+    if (b > max_blocks) b = max_blocks;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ---------------------------------------------------------------------------------
+// layout
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_nchw_to_nhwc(const float *__restrict__ x, T *__restrict__ y, int N, int C, int H, int W) {
+    int64_t total = (int64_t)N * C * H * W;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = i % C; int64_t r = i / C;
+        int w = r % W; r /= W;
+        int h = r % H; int n = r / H;
+        y[i] = from_f<T>(x[(((int64_t)n * C + c) * H + h) * W + w]);
+    }
+}
+int op_nchw_to_nhwc(const float *x, void *y, int dt, int N, int C, int H, int W, cudaStream_t s) {
+    int64_t total = (int64_t)N * C * H * W;
+    DISPATCH_DT(dt, T, B2_LAUNCH((k_nchw_to_nhwc<T>), grid_for(total, 256), 256, 0, s, x, (T *)y, N, C, H, W));
+    return 0;
+}
+template <typename T>
+__global__ void k_nhwc_to_nchw(const T *__restrict__ x, float *__restrict__ y, int N, int C, int H, int W) {
+    int64_t total = (int64_t)N * C * H * W;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int w = i % W; int64_t r = i / W;
+        int h = r % H; r /= H;
+        int c = r % C; int n = r / C;
+        y[i] = to_f<T>(x[(((int64_t)n * H + h) * W + w) * C + c]);
+    }
+}
+int op_nhwc_to_nchw_f32(const void *x, int dt, float *y, int N, int C, int H, int W, cudaStream_t s) {
+    int64_t total = (int64_t)N * C * H * W;
+    DISPATCH_DT(dt, T, B2_LAUNCH((k_nhwc_to_nchw<T>), grid_for(total, 256), 256, 0, s, (const T *)x, y, N, C, H, W));
+    return 0;
+}
+__global__ void k_f32_to_bf16(const float *__restrict__ x, bf16 *__restrict__ y, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = __float2bfloat16_rn(x[i]);
+}
+int op_f32_to_bf16(const float *x, bf16 *y, int64_t n, cudaStream_t s) {
+    B2_LAUNCH(k_f32_to_bf16, grid_for(n, 256), 256, 0, s, x, y, n);
+    return 0;
+}
+__global__ void k_f32_to_bf16_padded(const float *__restrict__ x, bf16 *__restrict__ y, int64_t rows, int k, int kpad) {
+    int64_t total = rows * kpad;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / kpad; int c = i - r * kpad;
+        y[i] = c < k ? __float2bfloat16_rn(x[r * k + c]) : __float2bfloat16_rn(0.f);
+    }
+}
+int op_f32_to_bf16_padded(const float *x, bf16 *y, int64_t rows, int k, int kpad, cudaStream_t s) {
+    B2_LAUNCH(k_f32_to_bf16_padded, grid_for(rows * kpad, 256), 256, 0, s, x, y, rows, k, kpad);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// BatchNorm.  x is [M][C] (NHWC flattened); per-channel statistics over M rows.
+// Block = 32 channels x 8 row lanes; grid = (C/32, row_blocks).
+// ---------------------------------------------------------------------------------
+int bn_row_blocks(int64_t M, int C) {
+    int gx = (C + 31) / 32;
+    int64_t want = (kNumSMs * 4 + gx - 1) / gx;
+    int64_t maxb = ceil_div(M, 8 * 4);   // at least 4 rows per thread
+    if (want > maxb) want = maxb;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256)
+k_bn_reduce(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy,
+            const float *__restrict__ mean, const float *__restrict__ invstd, bool relu,
+            int64_t M, int C, float *__restrict__ partial) {
+    // FWD: partial = {sum x, sum x^2};  BWD: partial = {sum g, sum g*xhat}
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const int64_t rows_per_block = (M + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = blockIdx.y * rows_per_block;
+    int64_t r1 = r0 + rows_per_block; if (r1 > M) r1 = M;
+    float s0 = 0.f, s1 = 0.f;
+    if (c < C) {
+        float mu = 0.f, is = 0.f;
+        if (BWD) { mu = mean[c]; is = invstd[c]; }
+        for (int64_t r = r0 + ty; r < r1; r += 8) {
+            float v = to_f<T>(x[r * C + c]);
+            if (!BWD) { s0 += v; s1 += v * v; }
+            else {
+                float g = to_f<T>(dy[r * C + c]);
+                if (relu && !(to_f<T>(y[r * C + c]) > 0.f)) g = 0.f;
+                s0 += g; s1 += g * ((v - mu) * is);
+            }
+        }
+    }
+    __shared__ float sh0[8][33], sh1[8][33];
+    sh0[ty][tx] = s0; sh1[ty][tx] = s1;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a += sh0[j][tx]; b += sh1[j][tx]; }
+        partial[((int64_t)blockIdx.y * 2 + 0) * C + c] = a;
+        partial[((int64_t)blockIdx.y * 2 + 1) * C + c] = b;
+    }
+}
+
+__global__ void k_bn_finalize_fwd(const float *__restrict__ partial, int nblk, int64_t M, int C, float eps,
+                                  float momentum, float *__restrict__ mean, float *__restrict__ invstd,
+                                  float *running_mean, float *running_var) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s0 = 0.0, s1 = 0.0;
+    for (int b = 0; b < nblk; ++b) { s0 += partial[((int64_t)b * 2) * C + c]; s1 += partial[((int64_t)b * 2 + 1) * C + c]; }
+    double mu = s0 / (double)M;
+    double var = s1 / (double)M - mu * mu;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)mu;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+k_bn_apply(const T *__restrict__ x, T *__restrict__ y, const T *__restrict__ res,
+           const float *__restrict__ mean, const float *__restrict__ invstd,
+           const float *__restrict__ gamma, const float *__restrict__ beta, bool relu, int64_t total, int C) {
+    for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * V; i < total; i += (int64_t)gridDim.x * blockDim.x * V) {
+        int c0 = i % C;
+        __align__(16) T xv[V], rv[V], ov[V];
+        *(uint4 *)xv = *(const uint4 *)(x + i);
+        if (res) *(uint4 *)rv = *(const uint4 *)(res + i);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            int c = c0 + j;
+            float v = ((to_f<T>(xv[j]) - mean[c]) * invstd[c]) * gamma[c] + beta[c];
+            if (res) v += to_f<T>(rv[j]);
+            if (relu) v = v > 0.f ? v : 0.f;
+            ov[j] = from_f<T>(v);
+        }
+        *(uint4 *)(y + i) = *(uint4 *)ov;
+    }
+}
+
+int op_bn_forward(const void *x, void *y, const void *res, int dt, int64_t M, int C, const float *gamma,
+                  const float *beta, float *running_mean, float *running_var, float eps, float momentum,
+                  bool relu, const BnWork &w, cudaStream_t s) {
+    B2_CHECK(C % 8 == 0, B2_ERR_ARG, "bn: C=%d must be a multiple of 8", C);
+    dim3 grid((C + 31) / 32, w.row_blocks);
+    DISPATCH_DT(dt, T, B2_LAUNCH((k_bn_reduce<T, false>), grid, 256, 0, s, (const T *)x, (const T *)nullptr,
+                                 (const T *)nullptr, (const float *)nullptr, (const float *)nullptr, false, M, C, w.partial));
+    B2_LAUNCH(k_bn_finalize_fwd, (C + 127) / 128, 128, 0, s, w.partial, w.row_blocks, M, C, eps, momentum, w.mean,
+              w.invstd, running_mean, running_var);
+    int64_t total = M * C;
+    if (dt == DT_F32) {
+        B2_LAUNCH((k_bn_apply<float, 4>), grid_for(total / 4, 256), 256, 0, s, (const float *)x, (float *)y,
+                  (const float *)res, w.mean, w.invstd, gamma, beta, relu, total, C);
+    } else {
+        B2_LAUNCH((k_bn_apply<bf16, 8>), grid_for(total / 8, 256), 256, 0, s, (const bf16 *)x, (bf16 *)y,
+                  (const bf16 *)res, w.mean, w.invstd, gamma, beta, relu, total, C);
+    }
+    return 0;
+}
+
+__global__ void k_bn_finalize_bwd(const float *__restrict__ partial, int nblk, int64_t M, int C,
+                                  const float *__restrict__ gamma, const float *__restrict__ invstd,
+                                  float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s0 = 0.0, s1 = 0.0;
+    for (int b = 0; b < nblk; ++b) { s0 += partial[((int64_t)b * 2) * C + c]; s1 += partial[((int64_t)b * 2 + 1) * C + c]; }
+    dbeta[c] = (float)s0;
+    dgamma[c] = (float)s1;
+    coef[c] = gamma[c] * invstd[c];
+    coef[C + c] = (float)(s0 / (double)M);
+    coef[2 * C + c] = (float)(s1 / (double)M);
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+k_bn_bwd_apply(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy, T *__restrict__ dx,
+               T *__restrict__ dres, const float *__restrict__ mean, const float *__restrict__ invstd,
+               const float *__restrict__ coef, bool relu, bool acc_dx, bool acc_dres, int64_t total, int C) {
+    for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * V; i < total; i += (int64_t)gridDim.x * blockDim.x * V) {
+        int c0 = i % C;
+        __align__(16) T xv[V], yv[V], gv[V], ov[V], rv[V], pv[V];
+        *(uint4 *)xv = *(const uint4 *)(x + i);
+        *(uint4 *)gv = *(const uint4 *)(dy + i);
+        if (relu) *(uint4 *)yv = *(const uint4 *)(y + i);
+        if (acc_dx) *(uint4 *)pv = *(const uint4 *)(dx + i);
+        if (dres && acc_dres) *(uint4 *)rv = *(const uint4 *)(dres + i);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            int c = c0 + j;
+            float g = to_f<T>(gv[j]);
+            if (relu && !(to_f<T>(yv[j]) > 0.f)) g = 0.f;
+            float xh = (to_f<T>(xv[j]) - mean[c]) * invstd[c];
+            float d = coef[c] * (g - coef[C + c] - xh * coef[2 * C + c]);
+            if (acc_dx) d += to_f<T>(pv[j]);
+            ov[j] = from_f<T>(d);
+            if (dres) {
+                float r = g;
+                if (acc_dres) r += to_f<T>(rv[j]);
+                rv[j] = from_f<T>(r);
+            }
+        }
+        *(uint4 *)(dx + i) = *(uint4 *)ov;
+        if (dres) *(uint4 *)(dres + i) = *(uint4 *)rv;
+    }
+}
+
+int op_bn_backward(const void *x, const void *y, const void *dy, void *dx, void *dres, int dt, int64_t M, int C,
+                   const float *gamma, float *dgamma, float *dbeta, bool relu, bool acc_dx, bool acc_dres,
+                   const BnWork &w, cudaStream_t s) {
+    dim3 grid((C + 31) / 32, w.row_blocks);
+    DISPATCH_DT(dt, T, B2_LAUNCH((k_bn_reduce<T, true>), grid, 256, 0, s, (const T *)x, (const T *)y, (const T *)dy,
+                                 w.mean, w.invstd, relu, M, C, w.partial));
+    B2_LAUNCH(k_bn_finalize_bwd, (C + 127) / 128, 128, 0, s, w.partial, w.row_blocks, M, C, gamma, w.invstd, dgamma,
+              dbeta, w.coef);
+    int64_t total = M * C;
+    if (dt == DT_F32) {
+        B2_LAUNCH((k_bn_bwd_apply<float, 4>), grid_for(total / 4, 256), 256, 0, s, (const float *)x, (const float *)y,
+                  (const float *)dy, (float *)dx, (float *)dres, w.mean, w.invstd, w.coef, relu, acc_dx, acc_dres, total, C);
+    } else {
+        B2_LAUNCH((k_bn_bwd_apply<bf16, 8>), grid_for(total / 8, 256), 256, 0, s, (const bf16 *)x, (const bf16 *)y,
+                  (const bf16 *)dy, (bf16 *)dx, (bf16 *)dres, w.mean, w.invstd, w.coef, relu, acc_dx, acc_dres, total, C);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// pooling
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_maxpool_fwd(const T *__restrict__ x, T *__restrict__ y, uint8_t *__restrict__ idx, int N, int Hi,
+                              int Wi, int C, int k, int stride, int pad, int Ho, int Wo, bool out_nchw) {
+    int64_t total = (int64_t)N * Ho * Wo * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = i % C; int64_t r = i / C;
+        int ow = r % Wo; r /= Wo;
+        int oh = r % Ho; int n = r / Ho;
+        float best = -INFINITY; int bi = 255;
+        for (int a = 0; a < k; ++a) {
+            int hi = oh * stride - pad + a;
+            if (hi < 0 || hi >= Hi) continue;
+            for (int b = 0; b < k; ++b) {
+                int wi = ow * stride - pad + b;
+                if (wi < 0 || wi >= Wi) continue;
+                float v = to_f<T>(x[(((int64_t)n * Hi + hi) * Wi + wi) * C + c]);
+                if (v > best || bi == 255) { best = v; bi = a * k + b; }   // first maximum wins (torch)
+            }
+        }
+        int64_t o = out_nchw ? (((int64_t)n * C + c) * Ho + oh) * Wo + ow : i;
+        y[o] = from_f<T>(best);
+        idx[i] = (uint8_t)bi;
+    }
+}
+int op_maxpool_forward(const void *x, void *y, uint8_t *idx, int dt, int N, int Hi, int Wi, int C, int k, int stride,
+                       int pad, int Ho, int Wo, bool out_nchw, cudaStream_t s) {
+    int64_t total = (int64_t)N * Ho * Wo * C;
+    DISPATCH_DT(dt, T, B2_LAUNCH((k_maxpool_fwd<T>), grid_for(total, 256), 256, 0, s, (const T *)x, (T *)y, idx, N, Hi,
+                                 Wi, C, k, stride, pad, Ho, Wo, out_nchw));
+    return 0;
+}
+template <typename T>
+__global__ void k_maxpool_bwd(const T *__restrict__ dy, const uint8_t *__restrict__ idx, T *__restrict__ dx, int N,
+                              int Hi, int Wi, int C, int k, int stride, int pad, int Ho, int Wo, bool out_nchw, bool acc) {
+    int64_t total = (int64_t)N * Hi * Wi * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = i % C; int64_t r = i / C;
+        int wi = r % Wi; r /= Wi;
+        int hi = r % Hi; int n = r / Hi;
+        float g = 0.f;
+        // windows (oh,ow) with oh*stride - pad <= hi <= oh*stride - pad + k - 1
+        int oh_lo = (hi + pad - k + 1 + stride - 1); oh_lo = oh_lo < 0 ? 0 : oh_lo / stride;
+        int oh_hi = (hi + pad) / stride; if (oh_hi > Ho - 1) oh_hi = Ho - 1;
+        int ow_lo = (wi + pad - k + 1 + stride - 1); ow_lo = ow_lo < 0 ? 0 : ow_lo / stride;
+        int ow_hi = (wi + pad) / stride; if (ow_hi > Wo - 1) ow_hi = Wo - 1;
+        for (int oh = oh_lo; oh <= oh_hi; ++oh)
+            for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+                int a = hi - (oh * stride - pad), b = wi - (ow * stride - pad);
+                int64_t oi = (((int64_t)n * Ho + oh) * Wo + ow) * C + c;
+                if (idx[oi] == (uint8_t)(a * k + b)) {
+                    int64_t o = out_nchw ? (((int64_t)n * C + c) * Ho + oh) * Wo + ow : oi;
+                    g += to_f<T>(dy[o]);
+                }
+            }
+        if (acc) g += to_f<T>(dx[i]);
+        dx[i] = from_f<T>(g);
+    }
+}
+int op_maxpool_backward(const void *dy, const uint8_t *idx, void *dx, int dt, int N, int Hi, int Wi, int C, int k,
+                        int stride, int pad, int Ho, int Wo, bool out_nchw, bool acc, cudaStream_t s) {
+    int64_t total = (int64_t)N * Hi * Wi * C;
+    DISPATCH_DT(dt, T, B2_LAUNCH((k_maxpool_bwd<T>), grid_for(total, 256), 256, 0, s, (const T *)dy, idx, (T *)dx, N, Hi,
+                                 Wi, C, k, stride, pad, Ho, Wo, out_nchw, acc));
+    return 0;
+}
+
+template <typename T>
+__global__ void k_avgpool_fwd(const T *__restrict__ x, float *__restrict__ y, int N, int HW, int C) {
+    int64_t total = (int64_t)N * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = i % C; int64_t n = i / C;
+        float s = 0.f;
+        for (int p = 0; p < HW; ++p) s += to_f<T>(x[(n * HW + p) * C + c]);
+        y[i] = s / (float)HW;
+    }
+}
+int op_avgpool_forward(const void *x, int xdt, float *y, int N, int HW, int C, cudaStream_t s) {
+    DISPATCH_DT(xdt, T, B2_LAUNCH((k_avgpool_fwd<T>), grid_for((int64_t)N * C, 256), 256, 0, s, (const T *)x, y, N, HW, C));
+    return 0;
+}
+template <typename T>
+__global__ void k_avgpool_bwd(const float *__restrict__ dy, T *__restrict__ dx, int N, int HW, int C, bool acc) {
+    int64_t total = (int64_t)N * HW * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = i % C; int64_t n = i / ((int64_t)HW * C);
+        float g = dy[n * C + c] / (float)HW;
+        if (acc) g += to_f<T>(dx[i]);
+        dx[i] = from_f<T>(g);
+    }
+}
+int op_avgpool_backward(const float *dy, void *dx, int xdt, int N, int HW, int C, bool acc, cudaStream_t s) {
+    DISPATCH_DT(xdt, T, B2_LAUNCH((k_avgpool_bwd<T>), grid_for((int64_t)N * HW * C, 256), 256, 0, s, dy, (T *)dx, N, HW, C, acc));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// pointwise
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_relu_mask(const T *__restrict__ y, T *__restrict__ dy, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (!(to_f<T>(y[i]) > 0.f)) dy[i] = from_f<T>(0.f);
+}
+int op_relu_mask(const void *y, void *dy, int dt, int64_t n, cudaStream_t s) {
+    DISPATCH_DT(dt, T, B2_LAUNCH((k_relu_mask<T>), grid_for(n, 256), 256, 0, s, (const T *)y, (T *)dy, n));
+    return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_bias_grad(const T *__restrict__ dy, int64_t M, int C, float *__restrict__ db) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    float s = 0.f;
+    if (c < C)
+        for (int64_t r = ty; r < M; r += 8) s += to_f<T>(dy[r * C + c]);
+    __shared__ float sh[8][33];
+    sh[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a += sh[j][tx];
+        db[c] = a;
+    }
+}
+int op_bias_grad(const void *dy, int dt, int64_t M, int C, float *db, cudaStream_t s) {
+    DISPATCH_DT(dt, T, B2_LAUNCH((k_bias_grad<T>), (C + 31) / 32, 256, 0, s, (const T *)dy, M, C, db));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// cross entropy (mean reduction) + softmax gradient, one kernel, one block
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_ce_loss_grad(const float *__restrict__ logits, const int64_t *__restrict__ labels, int B, int C,
+               float *__restrict__ loss, float *__restrict__ dlogits) {
+    float local = 0.f;
+    const float invB = 1.f / (float)B;
+    for (int r = threadIdx.x; r < B; r += blockDim.x) {
+        const float *row = logits + (int64_t)r * C;
+        float mx = -INFINITY;
+        for (int j = 0; j < C; ++j) mx = fmaxf(mx, row[j]);
+        float se = 0.f;
+        for (int j = 0; j < C; ++j) se += expf(row[j] - mx);
+        float lse = logf(se);
+        int lab = (int)labels[r];
+        local += -(row[lab] - mx - lse);
+        if (dlogits) {
+            float *drow = dlogits + (int64_t)r * C;
+            for (int j = 0; j < C; ++j) {
+                float p = expf(row[j] - mx - lse);
+                drow[j] = (p - (j == lab ? 1.f : 0.f)) * invB;
+            }
+        }
+    }
+    __shared__ float sh[256];
+    sh[threadIdx.x] = local;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss = sh[0] * invB;
+}
+int op_ce_loss_grad(const float *logits, const int64_t *labels, int B, int C, float *loss, float *dlogits, cudaStream_t s) {
+    B2_CHECK(B > 0 && C > 0, B2_ERR_ARG, "ce: empty batch (B=%d, C=%d)", B, C);
+    B2_LAUNCH(k_ce_loss_grad, 1, 256, 0, s, logits, labels, B, C, loss, dlogits);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// SGD with momentum: 20 B/param of HBM traffic (16 on the first step)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_sgd(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, int64_t n, float lr, float mom,
+      float gscale, int first) {
+    int64_t n4 = n >> 2;
+    float4 *p4 = (float4 *)p; const float4 *g4 = (const float4 *)g; float4 *m4 = (float4 *)m;
+    // torch semantics (sgd.py:_single_tensor_sgd): buf.mul_(momentum).add_(grad) is two
+    // roundings; param.add_(buf, alpha=-lr) is one fused multiply-add.
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 gv = g4[i], pv = p4[i], mv;
+        if (gscale != 1.f) { gv.x = __fmul_rn(gv.x, gscale); gv.y = __fmul_rn(gv.y, gscale); gv.z = __fmul_rn(gv.z, gscale); gv.w = __fmul_rn(gv.w, gscale); }
+        if (first) mv = gv;
+        else {
+            mv = m4[i];
+            mv.x = __fadd_rn(__fmul_rn(mv.x, mom), gv.x); mv.y = __fadd_rn(__fmul_rn(mv.y, mom), gv.y);
+            mv.z = __fadd_rn(__fmul_rn(mv.z, mom), gv.z); mv.w = __fadd_rn(__fmul_rn(mv.w, mom), gv.w);
+        }
+        pv.x = fmaf(-lr, mv.x, pv.x); pv.y = fmaf(-lr, mv.y, pv.y); pv.z = fmaf(-lr, mv.z, pv.z); pv.w = fmaf(-lr, mv.w, pv.w);
+        m4[i] = mv; p4[i] = pv;
+    }
+    for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gv = gscale != 1.f ? __fmul_rn(g[i], gscale) : g[i];
+        float mv = first ? gv : __fadd_rn(__fmul_rn(m[i], mom), gv);
+        m[i] = mv; p[i] = fmaf(-lr, mv, p[i]);
+    }
+}
+int op_sgd(float *p, const float *g, float *m, int64_t n, float lr, float momentum, float gscale, int first, cudaStream_t s) {
+    if (n <= 0) return 0;
+    B2_CHECK(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0), B2_ERR_ARG,
+             "sgd: p/g/m must be 16-byte aligned");
+    B2_LAUNCH(k_sgd, grid_for(ceil_div(n, 4), 256, kNumSMs * 8), 256, 0, s, p, g, m, n, lr, momentum, gscale, first);
+    return 0;
+}
+
+}  // namespace b2

@@ -1,0 +1,151 @@
+/*
+ * b2ddp.h -- C-ABI of the B200-native data-parallel training path.
+ *
+ * Drop-in boundary for the hot path of rensortino/DDP-Tutorial
+ * (/root/reference/cifar_example_ddp.py:82-110).  The reference has no FFI of its
+ * own: every entry point below replaces the torch/NCCL call that the cited
+ * reference line dispatches to.  Plain C: raw device pointers, sizes, scalars and
+ * cudaStream_t passed as void*.  No torch types, no C++ types, nothing throws.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; b2_last_error() returns a
+ *     thread-local message for the last failing call on this thread;
+ *   - all compute entries are asynchronous and ordered on the `stream` argument;
+ *   - the caller owns every buffer it passes and keeps it alive until the stream
+ *     work completes; the library owns what it allocates (model workspaces, comm
+ *     arenas, graphs) and frees it in *_destroy / b2_comm_finalize;
+ *   - one host thread per rank-process.
+ */
+#ifndef B2DDP_H_
+#define B2DDP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK 0
+#define B2_ERR_CUDA (-1)
+#define B2_ERR_ARG (-2)
+#define B2_ERR_STATE (-3)
+#define B2_ERR_TIMEOUT (-4)
+#define B2_ERR_UNSUPPORTED (-5)
+
+/* model kinds: the reference's Net (cifar_example_ddp.py:23-40) and the two
+ * torchvision topologies BASELINE.json substitutes at cifar_example.py:60 */
+#define B2_MODEL_NET 0
+#define B2_MODEL_RESNET18 1
+#define B2_MODEL_RESNET50 2
+
+/* arithmetic mode: 0 = fp32 storage + fp32 FMA (parity mode), 1 = bf16
+ * activations / bf16 weight copies, fp32 accumulate, fp32 master weights */
+#define B2_PREC_FP32 0
+#define B2_PREC_BF16 1
+
+typedef struct b2_model b2_model; /* opaque */
+
+/* ---- library ------------------------------------------------------------- */
+int b2_version(void);
+const char *b2_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's
+ * gpu_launches claim); monotonically increasing. */
+int64_t b2_launch_count(void);
+
+/* ---- model: replaces Net()/resnetXX() + .to(gpu) (cifar_example_ddp.py:82) - */
+int b2_model_create(int kind, int batch, int num_classes, int precision, int device, b2_model **out);
+int b2_model_destroy(b2_model *m);
+/* flat parameter vector layout (what DDP would put in its buckets,
+ * reducer.hpp:347-349): number of fp32 elements, number of tensors */
+int64_t b2_model_param_count(const b2_model *m);
+int b2_model_num_tensors(const b2_model *m);
+/* i-th parameter tensor in torch named_parameters() order: name (static string),
+ * element offset in the flat vector, logical torch shape (rank<=4) and the
+ * storage strides (in elements) of that logical shape inside the flat vector --
+ * conv weights are stored O,H,W,I so their O,I,H,W view is a strided view. */
+int b2_model_tensor_info(const b2_model *m, int i, const char **name, int64_t *offset,
+                         int *rank, int64_t shape[4], int64_t stride[4]);
+/* buffers (BatchNorm running_mean / running_var, fp32; num_batches_tracked is a
+ * host-side counter): same query for the flat buffer vector */
+int64_t b2_model_buffer_count(const b2_model *m);
+int b2_model_num_buffers(const b2_model *m);
+int b2_model_buffer_info(const b2_model *m, int i, const char **name, int64_t *offset, int64_t *numel);
+int64_t b2_model_steps_tracked(const b2_model *m);
+/* bind caller-owned flat fp32 vectors (params, grads; buffers may be NULL) */
+int b2_model_bind(b2_model *m, float *params, float *grads, float *buffers);
+/* bf16 mode: refresh the bf16 compute copies of the weights from the fp32
+ * masters (done automatically by b2_sgd_step_model; call after loading params) */
+int b2_model_sync_weights(b2_model *m, void *stream);
+/* tell the model that the bound fp32 parameters changed behind its back (optimizer
+ * step, load_state_dict): bf16 compute copies are refreshed before the next forward */
+int b2_model_mark_weights_dirty(b2_model *m);
+/* net(inputs): cifar_example_ddp.py:104.  x is fp32 NCHW [batch,3,32,32] on the
+ * device; logits fp32 [batch,num_classes] */
+int b2_forward(b2_model *m, const float *x_nchw, float *logits, void *stream);
+/* loss.backward(): cifar_example_ddp.py:106.  dlogits fp32 [batch,num_classes];
+ * writes every parameter gradient into the bound flat grad vector */
+int b2_backward(b2_model *m, const float *dlogits, void *stream);
+/* debugging / parity: copy an internal activation (by op index) out as fp32 NCHW */
+int b2_model_num_ops(const b2_model *m);
+int b2_model_read_activation(b2_model *m, int op, int want_grad, float *out, int64_t capacity,
+                             int64_t *numel, int shape[4], void *stream);
+
+/* ---- criterion: nn.CrossEntropyLoss() fwd+bwd (cifar_example_ddp.py:85,105) -- */
+int b2_ce_loss_grad(const float *logits, const int64_t *labels, int batch, int classes,
+                    float *loss_out, float *dlogits, void *stream);
+
+/* ---- optimizer: optim.SGD(lr, momentum).step() (cifar_example_ddp.py:86,107) -- */
+/* p,g,m fp32 [n]; first_step!=0 => m = g (sgd.py:_single_tensor_sgd clones the
+ * grad on the first step), else m = momentum*m + g; p -= lr*m.  grad_scale
+ * multiplies g first (1/world or loss-scale inverse; pass 1.0f for none). */
+int b2_sgd(float *p, const float *g, float *m, int64_t n, float lr, float momentum,
+           float grad_scale, int first_step, void *stream);
+
+/* ---- peer-memory communicator: replaces init_process_group('nccl') + DDP's
+ * Reducer all-reduce (cifar_example_ddp.py:42-58,83; reducer.hpp:524) ---------- */
+#define B2_IPC_HANDLE_BYTES 64
+int b2_comm_init(int rank, int world, int device);
+int b2_comm_finalize(void);
+/* allocate `bytes` of peer-mappable device memory (library-owned) */
+int b2_comm_alloc(int64_t bytes, void **ptr);
+int b2_comm_free(void *ptr);
+/* export an IPC handle for a b2_comm_alloc'd pointer; import a peer's handle */
+int b2_comm_export(void *ptr, void *handle_out /* B2_IPC_HANDLE_BYTES */);
+int b2_comm_import(const void *handle, void **peer_ptr);
+int b2_comm_unimport(void *peer_ptr);
+/* register the per-rank buffers of one "channel": grads[w], params[w] and
+ * flags[w] (uint32 signal pads, >= B2_FLAG_WORDS words, zero-initialised) are the
+ * world-size arrays of mapped pointers (entry `rank` is the local one). */
+#define B2_FLAG_WORDS 1024
+int b2_comm_register(void *const *grads, void *const *params, void *const *flags, int64_t n_elems);
+/* dist.barrier() (cifar_example_ddp.py:58): flag barrier in peer memory */
+int b2_comm_barrier(void *stream);
+/* size in bytes of one rank's flag pad (== B2_FLAG_WORDS * 4) */
+int b2_comm_flag_bytes(void);
+/* synchronises the device and reports B2_ERR_TIMEOUT if any comm kernel gave up waiting
+ * for a peer flag (a rank died or the ranks' launch sequences diverged) */
+int b2_comm_check(void);
+/* plain all-reduce(sum) * scale of the registered grad buffer, in place on every
+ * rank (for the bandwidth sweep, BASELINE config 5).  algo: 0 auto, 1 one-shot,
+ * 2 two-shot */
+int b2_allreduce(int64_t n_elems, float scale, int algo, void *stream);
+/* same on the sub-range [offset, offset+n_elems) (offset % 4 == 0): one DDP bucket */
+int b2_allreduce_range(int64_t offset, int64_t n_elems, float scale, int algo, void *stream);
+/* fused: all-reduce(sum)/world of the registered grads + SGD-momentum update of
+ * the registered params (m is local, fp32 [n]): Reducer + optimizer.step() in one
+ * kernel (cifar_example_ddp.py:106-107). */
+int b2_allreduce_sgd(float *m, int64_t n_elems, float lr, float momentum, int first_step,
+                     int algo, void *stream);
+int b2_allreduce_sgd_range(float *m, int64_t offset, int64_t n_elems, float lr, float momentum,
+                           int first_step, int algo, void *stream);
+
+/* ---- CUDA-graph capture of a step (launch-latency removal) ---------------- */
+int b2_graph_begin(void *stream);
+int b2_graph_end(void *stream, void **graph_exec);
+int b2_graph_launch(void *graph_exec, void *stream);
+int b2_graph_destroy(void *graph_exec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2DDP_H_ */

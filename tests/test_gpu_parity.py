@@ -1,0 +1,203 @@
+"""GPU parity: the CUDA path (through the C-ABI, driven by the reference-shaped facade)
+against the CPU oracle on the same seeded inputs and against the committed golden vectors.
+
+Tolerances (floating point path, north_star: loss within 1e-3 over 50 steps):
+  Net, fp32            : loss 1e-4 abs over 50 steps, grads/params rtol 1e-3 atol 1e-5
+  ResNet-18, fp32 mode : step-0 loss 1e-4, loss curve 1e-3 abs over 20 steps (fixed batch)
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ddp_tutorial_b200 as b2
+from oracle import ref_step as O
+
+pytestmark = pytest.mark.gpu
+DEV = 0
+
+
+def _vp(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def run_b2(model, x, y, steps, fixed=True, gen=None, batch=None):
+    crit = b2.CrossEntropyLoss()
+    opt = b2.SGD(model.parameters(), lr=0.001, momentum=0.9)
+    losses, grads0 = [], None
+    for s in range(steps):
+        if not fixed and s > 0:
+            x, y = O.synthetic_batch(gen, batch)
+        xd, yd = x.to(DEV), y.to(DEV)
+        opt.zero_grad()
+        out = model(xd)
+        loss = crit(out, yd)
+        loss.backward()
+        if s == 0:
+            grads0 = {n: p.grad.detach().cpu().clone() for n, p in model.named_parameters()}
+        opt.step()
+        losses.append(loss.item())
+    return losses, grads0
+
+
+# ------------------------------------------------------------------ kernels through the C-ABI
+def test_ce_loss_grad_matches_oracle():
+    torch.manual_seed(0)
+    for B, Cc in ((4, 10), (512, 10), (33, 7), (1, 10)):
+        lg, y = torch.randn(B, Cc) * 3, torch.randint(0, Cc, (B,))
+        loss_ref, d_ref = O.cross_entropy_and_grad(lg, y)
+        lgd, yd = lg.to(DEV), y.to(DEV)
+        loss, d = torch.empty(1, device=DEV), torch.empty(B, Cc, device=DEV)
+        b2._lib.call("b2_ce_loss_grad", _vp(lgd), _vp(yd), B, Cc, _vp(loss), _vp(d), None)
+        torch.cuda.synchronize()
+        assert abs(float(loss) - float(loss_ref)) < 2e-6 * max(1, abs(float(loss_ref)))
+        np.testing.assert_allclose(d.cpu().numpy(), d_ref.numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_sgd_matches_oracle_bitwise_on_ragged_sizes():
+    torch.manual_seed(0)
+    for n in (1, 3, 4, 5, 1023, 62006, 1 << 20):
+        p0, g1, g2 = torch.randn(n), torch.randn(n), torch.randn(n)
+        q, m = p0.clone(), None
+        pd = p0.to(DEV).clone()
+        md = torch.zeros(n, device=DEV)
+        for i, g in enumerate((g1, g2)):
+            q, m = O.sgd_momentum_update(q, g, m)
+            gd = g.to(DEV)
+            b2._lib.call("b2_sgd", _vp(pd), _vp(gd), _vp(md), n, 0.001, 0.9, 1.0, 1 if i == 0 else 0, None)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(pd.cpu().numpy(), q.numpy(), rtol=0, atol=1.2e-7)
+        np.testing.assert_allclose(md.cpu().numpy(), m.numpy(), rtol=0, atol=2.4e-7)
+
+
+# ------------------------------------------------------------------ Net (the reference's model)
+def test_net_forward_backward_step0(golden_dir):
+    g = np.load(os.path.join(golden_dir, "net_b4_w1.npz"))
+    torch.manual_seed(0)
+    net = b2.Net().to(DEV)
+    for n, p in net.named_parameters():
+        assert np.array_equal(p.detach().cpu().numpy(), g["init." + n]), n
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    ref = O.net_forward(O.net_init(0), x)
+    out = net(x.to(DEV))
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=1e-5)
+    loss = b2.CrossEntropyLoss()(out, y.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - g["loss"][0]) < 1e-5
+    for n, p in net.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), g["grad0." + n], rtol=1e-3, atol=1e-6, err_msg=n)
+
+
+def test_net_50_steps_vs_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "net_b4_w1.npz"))
+    torch.manual_seed(0)
+    net = b2.Net().to(DEV)
+    losses, _ = run_b2(net, torch.from_numpy(g["x"]), torch.from_numpy(g["y"]), 50)
+    assert np.max(np.abs(np.array(losses) - g["loss"])) < 1e-4
+    for n, p in net.named_parameters():
+        np.testing.assert_allclose(p.detach().cpu().numpy(), g["final." + n], rtol=1e-3, atol=1e-5, err_msg=n)
+
+
+def test_net_fresh_batches_vs_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "net_b16_fresh.npz"))
+    torch.manual_seed(0)
+    net = b2.Net().to(DEV)
+    gen = O.data_generator(0)
+    x, y = O.synthetic_batch(gen, 16)
+    losses, _ = run_b2(net, x, y, 50, fixed=False, gen=gen, batch=16)
+    assert np.max(np.abs(np.array(losses) - g["loss"])) < 1e-4
+
+
+def test_net_batch128_vs_oracle():
+    r = O.train("net", seed=0, batch=128, steps=10)
+    torch.manual_seed(0)
+    net = b2.Net().to(DEV)
+    losses, grads0 = run_b2(net, r["x"], r["y"], 10)
+    assert np.max(np.abs(np.array(losses) - np.array(r["loss"]))) < 1e-4
+    for n, gr in r["grads0"]:
+        np.testing.assert_allclose(grads0[n].numpy(), gr.numpy(), rtol=2e-3, atol=1e-6, err_msg=n)
+
+
+def test_state_dict_round_trip_and_names():
+    torch.manual_seed(0)
+    net = b2.Net().to(DEV)
+    sd = net.state_dict()
+    assert list(sd) == [n for n, _ in O.NET_PARAM_SHAPES]
+    assert tuple(sd["conv1.weight"].shape) == (6, 3, 5, 5) and sd["conv1.weight"].is_contiguous()
+    other = b2.Net().to(DEV)
+    other.load_state_dict(sd)
+    for (n, a), (_, b) in zip(net.named_parameters(), other.named_parameters()):
+        assert torch.equal(a, b), n
+
+
+# ------------------------------------------------------------------ ResNet-18 (BASELINE configs)
+def _grad_report(grads0, ref_grads):
+    worst = []
+    for n, gr in ref_grads:
+        a, b = grads0[n].double(), gr.double()
+        err = float((a - b).abs().max() / (b.abs().max() + 1e-12))
+        worst.append((err, n))
+    worst.sort(reverse=True)
+    return worst
+
+
+@pytest.mark.parametrize("batch", [32])
+def test_resnet18_fp32_step0_grads(batch):
+    r = O.train("resnet18", seed=0, batch=batch, steps=1)
+    torch.manual_seed(0)
+    net = b2.resnet18(num_classes=10, precision="fp32").to(DEV)
+    losses, grads0 = run_b2(net, r["x"], r["y"], 1)
+    assert abs(losses[0] - r["loss"][0]) < 1e-4, (losses[0], r["loss"][0])
+    worst = _grad_report(grads0, r["grads0"])
+    assert worst[0][0] < 5e-3, worst[:8]
+
+
+def test_resnet18_fp32_loss_curve_vs_golden(golden_dir):
+    with open(os.path.join(golden_dir, "resnet18_b32.json")) as f:
+        g = json.load(f)
+    gen = O.data_generator(0)
+    x, y = O.synthetic_batch(gen, 32)
+    torch.manual_seed(0)
+    net = b2.resnet18(num_classes=10, precision="fp32").to(DEV)
+    losses, _ = run_b2(net, x, y, g["steps"])
+    err = np.abs(np.array(losses) - np.array(g["loss"]))
+    assert err[0] < 1e-4 and err.max() < 1e-3, err
+
+
+def test_resnet18_state_dict_keys_match_torchvision():
+    import torchvision
+    torch.manual_seed(0)
+    net = b2.resnet18(num_classes=10, precision="fp32").to(DEV)
+    ref = torchvision.models.resnet18(num_classes=10)
+    sd, rsd = net.state_dict(), ref.state_dict()
+    assert list(sd) == list(rsd)
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(rsd[k].shape), k
+
+
+def test_resnet50_fp32_step0():
+    r = O.train("resnet50", seed=0, batch=8, steps=1)
+    torch.manual_seed(0)
+    net = b2.resnet50(num_classes=10, precision="fp32").to(DEV)
+    losses, grads0 = run_b2(net, r["x"], r["y"], 1)
+    assert abs(losses[0] - r["loss"][0]) < 2e-4, (losses[0], r["loss"][0])
+    worst = _grad_report(grads0, r["grads0"])
+    assert worst[0][0] < 2e-2, worst[:8]
+
+
+def test_resnet18_bf16_step0_close():
+    """bf16 storage: step-0 loss within 3e-2 of fp32 oracle (SURVEY.md 0.5 measured 2e-3 for
+    bf16-autocast vs fp32; activations are stored in bf16 here as well)."""
+    r = O.train("resnet18", seed=0, batch=64, steps=1)
+    torch.manual_seed(0)
+    net = b2.resnet18(num_classes=10, precision="bf16").to(DEV)
+    losses, grads0 = run_b2(net, r["x"], r["y"], 1)
+    assert abs(losses[0] - r["loss"][0]) < 3e-2, (losses[0], r["loss"][0])
+    # gradient direction: cosine similarity of the flattened gradient
+    a = torch.cat([grads0[n].flatten() for n, _ in r["grads0"]]).double()
+    b = torch.cat([g.flatten() for _, g in r["grads0"]]).double()
+    cos = float((a @ b) / (a.norm() * b.norm()))
+    assert cos > 0.98, cos
