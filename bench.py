@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""Benchmark of the DDP-Tutorial hot path on B200 (BASELINE.json metric):
+images/sec, device-timed, max over ranks, ResNet-18 (torchvision topology, num_classes=10),
+synthetic CIFAR-shaped input, per-GPU batch 512, bf16 storage / fp32 accumulate + fp32 master.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference ...                           # the reference CPU loop
+
+One "step" = the reference's six statements (cifar_example_ddp.py:101-110): zero_grad,
+forward, criterion, backward, optimizer.step (fused with the gradient all-reduce when N>1).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = "resnet18"
+BATCH = 512                      # per GPU (BASELINE configs[1], configs[2])
+TRAIN_FLOP_PER_IMG = 217.28e6    # dense implicit-GEMM count, fprop+dgrad+wgrad
+METRIC = "images/sec (device-timed, max over ranks) ResNet-18 CIFAR-shape"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["hbm_gbs"], p["bf16_tflops"], p.get("bf16_tflops_sustained", p["bf16_tflops"]), "measured"
+    except Exception:
+        return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(gpu_index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------
+# reference arm: the reference's CPU loop (cifar_example.py:66-87 semantics) via the oracle
+# ----------------------------------------------------------------------------------------
+def cpu_reference_loop(batch: int, steps: int, warmup: int):
+    import torch
+    from oracle import ref_step as O       # the CPU baseline IS the oracle (kind="port")
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = O.make_model(MODEL, 0)
+    crit = torch.nn.CrossEntropyLoss()
+    opt = torch.optim.SGD(model.parameters(), lr=O.LR, momentum=O.MOMENTUM)
+    x, y = O.synthetic_batch(O.data_generator(0), batch)
+    t0 = None
+    for s in range(warmup + steps):
+        if s == warmup:
+            t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = crit(model(x), y)
+        loss.backward()
+        opt.step()
+        loss.item()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ips, ms, threads = cpu_reference_loop(BATCH, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{MODEL}(num_classes=10) train step, batch {BATCH}, 3x32x32 synthetic, SGD(0.001,0.9)",
+                   "where": "host CPU cores, torch CPU kernels (the reference's own code path: cifar_example.py:66-87)"},
+        "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps of batch {BATCH} after {args.warmup} warm-up"},
+        "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+# this repo's arm
+# ----------------------------------------------------------------------------------------
+def run_b2(args):
+    import torch
+    import ddp_tutorial_b200 as b2
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
+    ns = argparse.Namespace()
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):      # keep stdout to the one JSON line
+        b2.init_distributed(ns)
+    dev = ns.gpu
+    torch.cuda.set_device(dev)
+
+    torch.manual_seed(0)
+    net = b2.resnet18(num_classes=10, precision=args.precision).to(dev)
+    model = b2.DistributedDataParallel(net, device_ids=[dev]) if ns.distributed else net
+    criterion = b2.CrossEntropyLoss()
+    optimizer = b2.SGD(model.parameters(), lr=0.001, momentum=0.9)
+
+    gen = torch.Generator().manual_seed(1 + rank)
+    x_host = torch.randn(BATCH, 3, 32, 32, generator=gen).pin_memory()
+    y_host = torch.randint(0, 10, (BATCH,), generator=gen).pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+
+    def step_resident():
+        optimizer.zero_grad()
+        loss = criterion(model(x_dev), y_dev)
+        loss.backward()
+        optimizer.step()
+        return loss
+
+    def step_e2e():
+        xi = x_host.to(dev, non_blocking=True)
+        yi = y_host.to(dev, non_blocking=True)
+        optimizer.zero_grad()
+        loss = criterion(model(xi), yi)
+        loss.backward()
+        optimizer.step()
+        return loss.item()                     # device->host read of the step's result
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if ns.distributed:
+            b2.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(steps):
+            last = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if ns.distributed:
+            import torch.distributed as dist
+            t = torch.tensor([ms], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)       # gloo, host side, outside the timed region
+            ms = float(t[0])
+        sync_all()
+        return ms, last
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    launches0 = b2.lib().b2_launch_count()
+    sampler = ClockSampler(dev) if rank == 0 else None
+    ms, last = timed(step_resident, args.steps)
+    launches = b2.lib().b2_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    final_loss = last.item()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    # ---- roofline leg: events around every op of the dominant kernel class (separate pass)
+    roofline = None
+    if rank == 0:
+        e = net.engine
+        m = e._model(BATCH)
+        b2._lib.call("b2_model_profile", m.h, 1)
+        nprof = 3
+        for _ in range(nprof):
+            step_resident()
+        arr_d, arr_i = (C.c_double * 8), (C.c_int * 8)
+        pms, pfl, pby, pln = arr_d(), arr_d(), arr_d(), arr_i()
+        b2._lib.call("b2_model_profile_collect", m.h, pms, pfl, pby, pln)
+        b2._lib.call("b2_model_profile", m.h, 0)
+        cats = ["conv_fprop", "conv_dgrad", "conv_wgrad", "bn_fwd", "bn_bwd", "pool", "other"]
+        per = {c: {"ms_per_step": pms[i] / nprof, "gflop_per_step": pfl[i] / nprof / 1e9,
+                   "mb_per_step": pby[i] / nprof / 1e6, "ops_per_step": pln[i] // nprof} for i, c in enumerate(cats)}
+        hbm, tf_burst, tf_sus, src = _peaks()
+        conv_ms = sum(per[c]["ms_per_step"] for c in cats[:3])
+        conv_fl = sum(per[c]["gflop_per_step"] for c in cats[:3])
+        total_ms = sum(v["ms_per_step"] for v in per.values())
+        achieved = conv_fl / conv_ms if conv_ms > 0 else 0.0          # GFLOP/ms == TFLOP/s
+        roofline = {"bound": "tensor", "kernel": "conv implicit-GEMM (fprop+dgrad+wgrad launches of one step)",
+                    "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
+                    "peak_source": f"{src} (cuBLAS bf16 sustained)", "traffic": None,
+                    "share_of_step": conv_ms / total_ms if total_ms else None, "per_class": per}
+
+    if rank == 0:
+        n = args.gpus
+        ips = n * BATCH * args.steps / (ms / 1e3)
+        ips_e2e = n * BATCH * args.steps / (ms_e2e / 1e3)
+        cpu = None
+        if n == 1 and not args.no_cpu_baseline:
+            cips, cms, threads = cpu_reference_loop(128, 12, 3)      # BASELINE configs[0]: batch 128
+            cpu = {"value": cips, "unit": "images/sec", "cores": threads, "kind": "port",
+                   "sample": "cifar_example.py loop via oracle/ref_step.py, resnet18 batch 128, 12 steps after 3 warm-up"}
+        line = {
+            "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": n, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"resnet18(num_classes=10) training step, per-GPU batch {BATCH}, 3x32x32 synthetic "
+                                   f"(BASELINE configs[{1 if n == 1 else 2}])",
+                       "global_batch": n * BATCH, "parallelism": f"dp{n}",
+                       "precision": "bf16 activations+weight copies, fp32 accumulate, fp32 master+momentum"
+                       if args.precision == "bf16" else "fp32",
+                       "l2": "no explicit flush: one step streams >600 MB of activations/gradients/params, "
+                             "several times the 126 MB L2"},
+            "final_loss": final_loss,
+            "e2e": {"value": ips_e2e, "unit": "images/sec", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if ns.distributed:
+        b2.destroy()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b2", choices=["b2", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b2(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -102,6 +102,17 @@ int b2_model_mark_weights_dirty(b2_model *h) {
     h->m->weights_dirty = true;
     return 0;
 }
+int b2_model_profile(b2_model *h, int enable) {
+    B2_CHECK(h, B2_ERR_ARG, "NULL model");
+    h->m->profiling = enable != 0;
+    return 0;
+}
+int b2_model_profile_collect(b2_model *h, double *ms, double *flops, double *bytes, int *launches) {
+    GUARD_BEGIN
+    B2_CHECK(h && ms && flops && bytes && launches, B2_ERR_ARG, "profile_collect: NULL argument");
+    return h->m->prof_collect(ms, flops, bytes, launches);
+    GUARD_END
+}
 int b2_model_num_ops(const b2_model *h) { return h ? (int)h->m->ops.size() : 0; }
 int b2_model_read_activation(b2_model *h, int op, int want_grad, float *out, int64_t capacity, int64_t *numel,
                              int shape[4], void *stream) {

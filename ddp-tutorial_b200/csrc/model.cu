@@ -272,6 +272,34 @@ Model::~Model() {
 }
 
 // =================================================================================
+// profiling (events around each op; only when enabled -- never in the timed bench region)
+// =================================================================================
+int Model::prof_begin(int cat, double flops, double bytes, cudaStream_t s) {
+    if (!profiling) return -1;
+    ProfRec r{};
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    r.cat = cat; r.flops = flops; r.bytes = bytes;
+    cudaEventRecord(r.a, s);
+    prof.push_back(r);
+    return (int)prof.size() - 1;
+}
+void Model::prof_end(int h, cudaStream_t s) {
+    if (h >= 0) cudaEventRecord(prof[h].b, s);
+}
+int Model::prof_collect(double ms[PC_COUNT], double flops[PC_COUNT], double bytes[PC_COUNT], int launches[PC_COUNT]) {
+    for (int i = 0; i < PC_COUNT; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
+    B2_CUDA(cudaDeviceSynchronize());
+    for (ProfRec &r : prof) {
+        float t = 0.f;
+        B2_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.cat] += t; flops[r.cat] += r.flops; bytes[r.cat] += r.bytes; launches[r.cat] += 1;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    prof.clear();
+    return 0;
+}
+
+// =================================================================================
 // execution
 // =================================================================================
 int Model::sync_weights(cudaStream_t s) {
@@ -289,14 +317,20 @@ int Model::forward(const float *x_nchw, float *logits, cudaStream_t s) {
     for (Op &o : ops) {
         Tensor &to = tensors[o.out];
         switch (o.type) {
-        case OP_INPUT:
+        case OP_INPUT: {
+            int ph = prof_begin(PC_OTHER, 0, to.numel * (4.0 + dt_size(to.dt)), s);
             B2_TRY(op_nchw_to_nhwc(x_nchw, to.val, to.dt, to.N, to.C, to.H, to.W, s));
+            prof_end(ph, s);
             break;
+        }
         case OP_CONV: {
             Tensor &ti = tensors[o.in];
             const void *w = o.wdt == DT_BF16 ? (const void *)o.wcopy : (const void *)(p_params + o.w_off);
             const float *bias = o.b_off >= 0 ? p_params + o.b_off : nullptr;
+            int ph = prof_begin(PC_CONV_FPROP, 2.0 * o.g.M() * o.g.Co * o.g.K(),
+                                ti.numel * (double)dt_size(ti.dt) + to.numel * (double)dt_size(to.dt) + (double)o.g.Co * o.g.K() * dt_size(o.wdt), s);
             B2_TRY(conv_simt_fprop(o.g, ti.val, ti.dt, w, o.wdt, o.wpitch, bias, o.relu, to.val, to.dt, s));
+            prof_end(ph, s);
             if (o.out == logits_tensor && logits)
                 B2_CUDA(cudaMemcpyAsync(logits, to.val, to.numel * 4, cudaMemcpyDeviceToDevice, s));
             break;
@@ -304,15 +338,19 @@ int Model::forward(const float *x_nchw, float *logits, cudaStream_t s) {
         case OP_BN: {
             Tensor &ti = tensors[o.in];
             int64_t M = (int64_t)ti.N * ti.H * ti.W;
+            int ph = prof_begin(PC_BN_FWD, 0, ti.numel * (double)dt_size(ti.dt) * (o.res >= 0 ? 4.0 : 3.0), s);
             B2_TRY(op_bn_forward(ti.val, to.val, o.res >= 0 ? tensors[o.res].val : nullptr, ti.dt, M, ti.C,
                                  p_params + o.w_off, p_params + o.b_off, p_buffers ? p_buffers + o.rm_off : nullptr,
                                  p_buffers ? p_buffers + o.rv_off : nullptr, 1e-5f, 0.1f, o.relu, o.bn, s));
+            prof_end(ph, s);
             break;
         }
         case OP_MAXPOOL: {
             Tensor &ti = tensors[o.in];
+            int ph = prof_begin(PC_POOL, 0, (ti.numel + to.numel) * (double)dt_size(ti.dt) + to.numel, s);
             B2_TRY(op_maxpool_forward(ti.val, to.val, o.idx, ti.dt, o.g.N, o.g.Hi, o.g.Wi, o.g.Ci, o.g.kh, o.g.stride,
                                       o.g.pad, o.g.Ho, o.g.Wo, o.out_nchw, s));
+            prof_end(ph, s);
             break;
         }
         case OP_AVGPOOL: {
@@ -340,18 +378,26 @@ int Model::backward(const float *dlogits, cudaStream_t s) {
             if (o.relu) B2_TRY(op_relu_mask(to.val, to.grad, to.dt, to.numel, s));
             if (o.b_off >= 0) B2_TRY(op_bias_grad(to.grad, to.dt, o.g.M(), o.g.Co, p_grads + o.b_off, s));
             B2_CHECK(to.dt == ti.dt, B2_ERR_STATE, "conv backward: mixed activation types");
+            const double cflops = 2.0 * o.g.M() * o.g.Co * o.g.K();
+            const double cbytes = ti.numel * (double)dt_size(ti.dt) + to.numel * (double)dt_size(to.dt);
+            int ph = prof_begin(PC_CONV_WGRAD, cflops, cbytes + (double)o.g.Co * o.g.K() * 4, s);
             B2_TRY(conv_simt_wgrad(o.g, ti.val, to.grad, ti.dt, p_grads + o.w_off, wgrad_ws, wgrad_floats, s));
+            prof_end(ph, s);
             if (o.need_dgrad) {
                 const void *w = o.wdt == DT_BF16 ? (const void *)o.wcopy : (const void *)(p_params + o.w_off);
+                ph = prof_begin(PC_CONV_DGRAD, cflops, cbytes + (double)o.g.Co * o.g.K() * dt_size(o.wdt), s);
                 B2_TRY(conv_simt_dgrad(o.g, to.grad, to.dt, w, o.wdt, o.wpitch, ti.grad, o.acc_in, s));
+                prof_end(ph, s);
             }
             break;
         }
         case OP_BN: {
             int64_t M = (int64_t)ti.N * ti.H * ti.W;
+            int ph = prof_begin(PC_BN_BWD, 0, ti.numel * (double)dt_size(ti.dt) * (o.res >= 0 ? 7.0 : 6.0), s);
             B2_TRY(op_bn_backward(ti.val, to.val, to.grad, ti.grad, o.res >= 0 ? tensors[o.res].grad : nullptr, ti.dt, M,
                                   ti.C, p_params + o.w_off, p_grads + o.w_off, p_grads + o.b_off, o.relu, o.acc_in,
                                   o.acc_res, o.bn, s));
+            prof_end(ph, s);
             break;
         }
         case OP_MAXPOOL:

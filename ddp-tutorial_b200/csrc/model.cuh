@@ -29,6 +29,10 @@ struct Op {
     bf16 *wcopy;                 // bf16 mode: compute copy of the weights [Co][wpitch]
 };
 
+// per-launch-group profiling (bench.py's roofline leg): CUDA events around every op
+enum ProfCat { PC_CONV_FPROP = 0, PC_CONV_DGRAD, PC_CONV_WGRAD, PC_BN_FWD, PC_BN_BWD, PC_POOL, PC_OTHER, PC_COUNT };
+struct ProfRec { cudaEvent_t a, b; int cat; double flops, bytes; };
+
 struct ParamInfo { std::string name; int64_t offset, numel; int rank; int64_t shape[4], stride[4]; };
 struct BufferInfo { std::string name; int64_t offset, numel; };
 
@@ -45,6 +49,12 @@ struct Model {
     float *wgrad_ws = nullptr; size_t wgrad_floats = 0;
     bool weights_dirty = true;
     int64_t steps_tracked = 0;
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    int prof_begin(int cat, double flops, double bytes, cudaStream_t s);
+    void prof_end(int h, cudaStream_t s);
+    int prof_collect(double ms[PC_COUNT], double flops[PC_COUNT], double bytes[PC_COUNT], int launches[PC_COUNT]);
 
     static int create(int kind, int batch, int num_classes, int precision, int device, Model **out);
     ~Model();

@@ -85,6 +85,20 @@ int b2_forward(b2_model *m, const float *x_nchw, float *logits, void *stream);
 /* loss.backward(): cifar_example_ddp.py:106.  dlogits fp32 [batch,num_classes];
  * writes every parameter gradient into the bound flat grad vector */
 int b2_backward(b2_model *m, const float *dlogits, void *stream);
+/* measurement: when enabled, forward/backward bracket every op with CUDA events on the
+ * launching stream; collect() synchronises and returns, per category (B2_PROF_*), the summed
+ * milliseconds, algorithmic FLOPs, algorithmic bytes and number of op launches since the last
+ * collect.  Arrays have B2_PROF_COUNT entries. */
+#define B2_PROF_CONV_FPROP 0
+#define B2_PROF_CONV_DGRAD 1
+#define B2_PROF_CONV_WGRAD 2
+#define B2_PROF_BN_FWD 3
+#define B2_PROF_BN_BWD 4
+#define B2_PROF_POOL 5
+#define B2_PROF_OTHER 6
+#define B2_PROF_COUNT 7
+int b2_model_profile(b2_model *m, int enable);
+int b2_model_profile_collect(b2_model *m, double *ms, double *flops, double *bytes, int *launches);
 /* debugging / parity: copy an internal activation (by op index) out as fp32 NCHW */
 int b2_model_num_ops(const b2_model *m);
 int b2_model_read_activation(b2_model *m, int op, int want_grad, float *out, int64_t capacity,

@@ -1,0 +1,66 @@
+"""Run under torchrun on W GPUs: the DDP drop-in (peer-memory all-reduce fused with SGD)
+against the oracle's world=W restatement.  Prints 'DDP_CHECK OK' on rank 0.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29533 tools/ddp_check.py [net|resnet18] [steps]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import ddp_tutorial_b200 as b2
+from oracle import ref_step as O
+
+name = sys.argv[1] if len(sys.argv) > 1 else "net"
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+B = 4 if name == "net" else 16
+args = argparse.Namespace()
+b2.init_distributed(args)
+W, rank = args.world_size, int(os.environ["RANK"])
+r = O.train(name, seed=0, batch=B, steps=steps, world=W, dtype=torch.float32)
+torch.manual_seed(0 if rank == 0 else 1234 + rank)          # rank 0's init must win
+net = (b2.Net() if name == "net" else getattr(b2, name)(num_classes=10, precision="fp32")).to(args.gpu)
+net = b2.DistributedDataParallel(net, device_ids=[args.gpu])
+crit = b2.CrossEntropyLoss()
+opt = b2.SGD(net.parameters(), lr=0.001, momentum=0.9)
+x = r["x"][rank * B:(rank + 1) * B].to(args.gpu)
+y = r["y"][rank * B:(rank + 1) * B].to(args.gpu)
+losses = []
+for s in range(steps):
+    opt.zero_grad()
+    loss = crit(net(x), y)
+    loss.backward()
+    opt.step()
+    losses.append(loss.item())
+torch.cuda.synchronize()
+from ddp_tutorial_b200 import parallel
+parallel.check()
+tol = 1e-4 if name == "net" else 2e-3
+ok = True
+if rank == 0:
+    err = np.max(np.abs(np.array(losses) - np.array(r["loss"])))
+    print("rank0 loss err", err, losses[:3], r["loss"][:3])
+    ok &= err < tol
+sd = net.state_dict()
+perr = 0.0
+for n, t in r["final"]:
+    a = sd["module." + n].cpu()
+    perr = max(perr, float((a - t).abs().max() / (t.abs().max() + 1e-12)))
+print(f"rank {rank} max param rel err {perr:.3e}")
+ok &= perr < (1e-4 if name == "net" else 5e-3)
+# replicas bit-identical
+import torch.distributed as dist
+flat = net.module.engine.flat_params.cpu()
+gathered = [torch.zeros_like(flat) for _ in range(W)]
+dist.all_gather(gathered, flat)
+same = all(torch.equal(gathered[0], g) for g in gathered)
+print(f"rank {rank} replicas identical: {same}")
+ok &= same
+b2.destroy()
+if rank == 0:
+    print("DDP_CHECK OK" if ok else "DDP_CHECK FAILED")
+sys.exit(0 if ok else 1)
