@@ -86,10 +86,26 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------
 # reference arm: the reference's CPU loop (cifar_example.py:66-87 semantics) via the oracle
 # ----------------------------------------------------------------------------------------
+def usable_cores() -> int:
+    """Host threads this process can really use: affinity mask capped by the cgroup CPU quota
+    (os.cpu_count() reports the whole machine and oversubscribes a container)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_reference_loop(batch: int, steps: int, warmup: int):
     import torch
     from oracle import ref_step as O       # the CPU baseline IS the oracle (kind="port")
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(min(usable_cores(), 64))
+    sys.stderr.write(f"[bench] cpu reference: os.cpu_count()={os.cpu_count()} usable={usable_cores()} "
+                     f"torch threads={torch.get_num_threads()}\n")
     model = O.make_model(MODEL, 0)
     crit = torch.nn.CrossEntropyLoss()
     opt = torch.optim.SGD(model.parameters(), lr=O.LR, momentum=O.MOMENTUM)
