@@ -2,6 +2,7 @@
 // reference line each entry replaces.  Nothing throws across this boundary.
 #include <stdarg.h>
 #include <new>
+#include <algorithm>
 
 #include "model.cuh"
 
@@ -77,6 +78,7 @@ int b2_model_bind(b2_model *h, float *params, float *grads, float *buffers) {
     B2_CHECK(((uintptr_t)params % 16) == 0 && ((uintptr_t)grads % 16) == 0, B2_ERR_ARG, "b2_model_bind: vectors must be 16-byte aligned");
     h->m->p_params = params; h->m->p_grads = grads; h->m->p_buffers = buffers;
     h->m->weights_dirty = true;
+    h->m->plans_ready = false;
     return 0;
 }
 int b2_model_sync_weights(b2_model *h, void *stream) {
@@ -149,6 +151,40 @@ int b2_sgd(float *p, const float *g, float *m, int64_t n, float lr, float moment
     if (n == 0) return 0;
     B2_CHECK(p && g && m, B2_ERR_ARG, "b2_sgd: NULL argument");
     return op_sgd(p, g, m, n, lr, momentum, grad_scale, first_step, (cudaStream_t)stream);
+    GUARD_END
+}
+
+// ---- kernel-level test entry: one conv pass through the tcgen05 path or the SIMT path -------
+int b2_conv_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, int pad, int mode, int use_umma, int acc,
+                 const void *x_bf16, const float *w_master, const void *dy_bf16, void *out, void *stream) {
+    GUARD_BEGIN
+    cudaStream_t s = (cudaStream_t)stream;
+    ConvGeom g{};
+    g.N = N; g.Hi = Hi; g.Wi = Wi; g.Ci = Ci; g.Co = Co; g.kh = g.kw = k; g.stride = stride; g.pad = pad;
+    g.Ho = (Hi + 2 * pad - k) / stride + 1; g.Wo = (Wi + 2 * pad - k) / stride + 1;
+    const int taps = k * k;
+    bf16 *w = nullptr, *wt = nullptr; float *ws = nullptr;
+    size_t wsf = std::max(umma_wgrad_workspace(g), conv_simt_wgrad_workspace(g)) + 64;
+    B2_CUDA(cudaMalloc(&w, (size_t)Co * taps * Ci * 2));
+    B2_CUDA(cudaMalloc(&wt, (size_t)Co * taps * Ci * 2));
+    B2_CUDA(cudaMalloc(&ws, wsf * 4));
+    int rc = umma_prepare_weights(w_master, w, wt, Co, Ci, taps, s);
+    if (rc == 0) {
+        if (use_umma) {
+            if (!umma_conv_eligible(g)) { set_error("conv_test: shape not eligible for the tcgen05 path"); rc = B2_ERR_UNSUPPORTED; }
+            else if (mode == 0) { UmmaConvPlan pl; rc = umma_plan_fprop(g, (const bf16 *)x_bf16, w, (bf16 *)out, &pl); if (!rc) rc = umma_conv_launch(pl, s); }
+            else if (mode == 1) { UmmaConvPlan pl; rc = umma_plan_dgrad(g, (const bf16 *)dy_bf16, wt, (bf16 *)out, acc != 0, &pl); if (!rc) rc = umma_conv_launch(pl, s); }
+            else { UmmaWgradPlan pl; rc = umma_plan_wgrad(g, (const bf16 *)x_bf16, (const bf16 *)dy_bf16, (float *)out, ws, wsf, &pl); if (!rc) rc = umma_wgrad_launch(pl, s); }
+        } else {
+            if (mode == 0) rc = conv_simt_fprop(g, x_bf16, DT_BF16, w, DT_BF16, g.K(), nullptr, false, out, DT_BF16, s);
+            else if (mode == 1) rc = conv_simt_dgrad(g, dy_bf16, DT_BF16, w, DT_BF16, g.K(), out, acc != 0, s);
+            else rc = conv_simt_wgrad(g, x_bf16, dy_bf16, DT_BF16, (float *)out, ws, wsf, s);
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(w); cudaFree(wt); cudaFree(ws);
+    if (rc == 0 && e != cudaSuccess) { set_error("conv_test: %s", cudaGetErrorString(e)); rc = B2_ERR_CUDA; }
+    return rc;
     GUARD_END
 }
 

@@ -1,0 +1,75 @@
+// tcgen05 / TMA implicit-GEMM convolution for NHWC bf16 activations (fprop, dgrad, wgrad).
+#pragma once
+#include <cuda.h>
+#include "ops.cuh"
+
+namespace b2 {
+
+constexpr int kMaxTaps = 9;
+
+// One group of filter taps sharing an output-pixel lattice: fprop / stride-1 dgrad have a
+// single class (all taps, dense outputs); a stride-2 dgrad has one class per output parity.
+struct TapClass {
+    int ntaps;
+    int oh, ow;                 // output lattice offset (pixel = box_pixel * os + (oh, ow))
+    int dh[kMaxTaps], dw[kMaxTaps];   // source-box coordinate offsets of each tap
+    int kofs[kMaxTaps];         // element offset of the tap's 64-wide K slices in the B matrix
+};
+
+struct TapGemmParams {
+    int nclasses;
+    TapClass cls[4];
+    int c_chunks;               // source channels / 64
+    int BW, BH, BN, h_blocks;   // 128-pixel tile = BN images x BH rows x BW cols (box space)
+    int a_hstep;                // source rows per box row (conv stride for fprop, else 1)
+    int out_H, out_W, out_C, os;
+    bf16 *out;
+    int acc;                    // 1: out += result (bf16 read-modify-write)
+    float *stats;               // optional [2][out_C] per-channel sum / sum of squares (atomics); may be null
+};
+
+struct UmmaConvPlan {
+    CUtensorMap a_map, b_map;
+    TapGemmParams p;
+    dim3 grid;
+    double flops;               // executed FLOPs (dead taps skipped)
+    bool valid;
+};
+
+struct WgradParams {
+    int ntaps_alive;
+    int tap_id[kMaxTaps];       // index of each live tap in the (kh,kw) grid -> K offset tap_id*Ci
+    int dh[kMaxTaps], dw[kMaxTaps];
+    int c_chunks, Ci, Co, K;    // K = taps*Ci (row pitch of dW)
+    int BW, BH, BN, h_blocks, a_hstep;
+    int pix_tiles, tiles_per_split, splits;
+    int m_boxes;                // Co tile = 64*m_boxes (1 or 2)
+    float *out;                 // dW (splits == 1) or partial buffer [splits][Co][K]
+};
+
+struct UmmaWgradPlan {
+    CUtensorMap x_map, dy_map;
+    WgradParams p;
+    dim3 grid;
+    float *dw;
+    bool need_zero;             // dead taps exist: dW must be zeroed first
+    double flops;
+    bool valid;
+};
+
+bool umma_conv_eligible(const ConvGeom &g);
+int umma_init();   // resolves the driver entry point for tensor-map encoding
+int umma_plan_fprop(const ConvGeom &g, const bf16 *x, const bf16 *w, bf16 *y, UmmaConvPlan *plan);
+int umma_plan_dgrad(const ConvGeom &g, const bf16 *dy, const bf16 *wt, bf16 *dx, bool acc, UmmaConvPlan *plan);
+int umma_conv_launch(const UmmaConvPlan &plan, cudaStream_t s);
+size_t umma_wgrad_workspace(const ConvGeom &g);
+int umma_plan_wgrad(const ConvGeom &g, const bf16 *x, const bf16 *dy, float *dw, float *partial, size_t partial_floats,
+                    UmmaWgradPlan *plan);
+int umma_wgrad_launch(const UmmaWgradPlan &plan, cudaStream_t s);
+// bf16 compute copies of a conv weight from the fp32 master (O,H,W,I):
+//   w  [Co][taps*Ci]   (fprop B operand, K = (tap, ci))
+//   wt [Ci][taps*Co]   (dgrad B operand, K = (tap, co))
+int umma_prepare_weights(const float *master, bf16 *w, bf16 *wt, int Co, int Ci, int taps, cudaStream_t s);
+int reduce_partials(const float *part, float *out, int64_t n, int splits, cudaStream_t s);
+
+}  // namespace b2

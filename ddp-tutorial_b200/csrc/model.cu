@@ -216,7 +216,7 @@ int Model::finalize() {
         voff[i] = reserve(t.numel * dt_size(t.dt));
         goff[i] = reserve(t.numel * dt_size(t.dt));
     }
-    struct Scratch { size_t partial, mean, invstd, coef, idx, wcopy; };
+    struct Scratch { size_t partial, mean, invstd, coef, idx, wcopy, wt; };
     std::vector<Scratch> so(ops.size());
     size_t wg_floats = 0;
     for (size_t i = 0; i < ops.size(); ++i) {
@@ -235,6 +235,11 @@ int Model::finalize() {
             if (tensors[o.in].dt == DT_BF16) {
                 o.wdt = DT_BF16; o.wpitch = (o.g.K() + 63) / 64 * 64;
                 so[i].wcopy = reserve((size_t)o.g.Co * o.wpitch * 2);
+                o.use_umma = conv_impl == 1 && tensors[o.out].dt == DT_BF16 && !o.relu && o.b_off < 0 && umma_conv_eligible(o.g);
+                if (o.use_umma) {
+                    so[i].wt = reserve((size_t)o.g.Ci * o.g.kh * o.g.kw * o.g.Co * 2);
+                    wg_floats = std::max(wg_floats, umma_wgrad_workspace(o.g));
+                }
             }
         }
     }
@@ -254,6 +259,7 @@ int Model::finalize() {
             o.idx = (uint8_t *)(base + so[i].idx);
         } else if (o.type == OP_CONV && o.wdt == DT_BF16) {
             o.wcopy = (bf16 *)(base + so[i].wcopy);
+            if (o.use_umma) o.wt = (bf16 *)(base + so[i].wt);
         }
     }
     wgrad_ws = (float *)(base + wg_off);
@@ -305,14 +311,36 @@ int Model::prof_collect(double ms[PC_COUNT], double flops[PC_COUNT], double byte
 int Model::sync_weights(cudaStream_t s) {
     B2_CHECK(p_params, B2_ERR_STATE, "model: parameters not bound");
     for (Op &o : ops)
-        if (o.type == OP_CONV && o.wdt == DT_BF16)
-            B2_TRY(op_f32_to_bf16_padded(p_params + o.w_off, o.wcopy, o.g.Co, o.g.K(), o.wpitch, s));
+        if (o.type == OP_CONV && o.wdt == DT_BF16) {
+            if (o.use_umma)
+                B2_TRY(umma_prepare_weights(p_params + o.w_off, o.wcopy, o.need_dgrad ? o.wt : nullptr, o.g.Co, o.g.Ci,
+                                            o.g.kh * o.g.kw, s));
+            else
+                B2_TRY(op_f32_to_bf16_padded(p_params + o.w_off, o.wcopy, o.g.Co, o.g.K(), o.wpitch, s));
+        }
     weights_dirty = false;
+    return 0;
+}
+
+int Model::build_plans() {
+    for (Op &o : ops) {
+        if (o.type != OP_CONV || !o.use_umma) continue;
+        Tensor &ti = tensors[o.in], &to = tensors[o.out];
+        B2_TRY(umma_plan_fprop(o.g, (const bf16 *)ti.val, o.wcopy, (bf16 *)to.val, &o.fplan));
+        if (o.need_dgrad) {
+            // a 1x1 stride-2 dgrad only touches even pixels: zero-fill first when it is the first writer
+            bool sparse = o.g.stride == 2 && o.g.kh == 1;
+            B2_TRY(umma_plan_dgrad(o.g, (const bf16 *)to.grad, o.wt, (bf16 *)ti.grad, o.acc_in || sparse, &o.dplan));
+        }
+        B2_TRY(umma_plan_wgrad(o.g, (const bf16 *)ti.val, (const bf16 *)to.grad, p_grads + o.w_off, wgrad_ws, wgrad_floats, &o.wplan));
+    }
+    plans_ready = true;
     return 0;
 }
 
 int Model::forward(const float *x_nchw, float *logits, cudaStream_t s) {
     B2_CHECK(p_params && p_grads, B2_ERR_STATE, "model: parameters/gradients not bound (b2_model_bind)");
+    if (!plans_ready) B2_TRY(build_plans());
     if (weights_dirty) B2_TRY(sync_weights(s));
     for (Op &o : ops) {
         Tensor &to = tensors[o.out];
@@ -327,9 +355,10 @@ int Model::forward(const float *x_nchw, float *logits, cudaStream_t s) {
             Tensor &ti = tensors[o.in];
             const void *w = o.wdt == DT_BF16 ? (const void *)o.wcopy : (const void *)(p_params + o.w_off);
             const float *bias = o.b_off >= 0 ? p_params + o.b_off : nullptr;
-            int ph = prof_begin(PC_CONV_FPROP, 2.0 * o.g.M() * o.g.Co * o.g.K(),
+            int ph = prof_begin(PC_CONV_FPROP, o.use_umma ? o.fplan.flops : 2.0 * o.g.M() * o.g.Co * o.g.K(),
                                 ti.numel * (double)dt_size(ti.dt) + to.numel * (double)dt_size(to.dt) + (double)o.g.Co * o.g.K() * dt_size(o.wdt), s);
-            B2_TRY(conv_simt_fprop(o.g, ti.val, ti.dt, w, o.wdt, o.wpitch, bias, o.relu, to.val, to.dt, s));
+            if (o.use_umma) B2_TRY(umma_conv_launch(o.fplan, s));
+            else B2_TRY(conv_simt_fprop(o.g, ti.val, ti.dt, w, o.wdt, o.wpitch, bias, o.relu, to.val, to.dt, s));
             prof_end(ph, s);
             if (o.out == logits_tensor && logits)
                 B2_CUDA(cudaMemcpyAsync(logits, to.val, to.numel * 4, cudaMemcpyDeviceToDevice, s));
@@ -380,13 +409,20 @@ int Model::backward(const float *dlogits, cudaStream_t s) {
             B2_CHECK(to.dt == ti.dt, B2_ERR_STATE, "conv backward: mixed activation types");
             const double cflops = 2.0 * o.g.M() * o.g.Co * o.g.K();
             const double cbytes = ti.numel * (double)dt_size(ti.dt) + to.numel * (double)dt_size(to.dt);
-            int ph = prof_begin(PC_CONV_WGRAD, cflops, cbytes + (double)o.g.Co * o.g.K() * 4, s);
-            B2_TRY(conv_simt_wgrad(o.g, ti.val, to.grad, ti.dt, p_grads + o.w_off, wgrad_ws, wgrad_floats, s));
+            int ph = prof_begin(PC_CONV_WGRAD, o.use_umma ? o.wplan.flops : cflops, cbytes + (double)o.g.Co * o.g.K() * 4, s);
+            if (o.use_umma) B2_TRY(umma_wgrad_launch(o.wplan, s));
+            else B2_TRY(conv_simt_wgrad(o.g, ti.val, to.grad, ti.dt, p_grads + o.w_off, wgrad_ws, wgrad_floats, s));
             prof_end(ph, s);
             if (o.need_dgrad) {
                 const void *w = o.wdt == DT_BF16 ? (const void *)o.wcopy : (const void *)(p_params + o.w_off);
-                ph = prof_begin(PC_CONV_DGRAD, cflops, cbytes + (double)o.g.Co * o.g.K() * dt_size(o.wdt), s);
-                B2_TRY(conv_simt_dgrad(o.g, to.grad, to.dt, w, o.wdt, o.wpitch, ti.grad, o.acc_in, s));
+                ph = prof_begin(PC_CONV_DGRAD, o.use_umma ? o.dplan.flops : cflops, cbytes + (double)o.g.Co * o.g.K() * dt_size(o.wdt), s);
+                if (o.use_umma) {
+                    if (o.g.stride == 2 && o.g.kh == 1 && !o.acc_in)
+                        B2_CUDA(cudaMemsetAsync(ti.grad, 0, ti.numel * dt_size(ti.dt), s));
+                    B2_TRY(umma_conv_launch(o.dplan, s));
+                } else {
+                    B2_TRY(conv_simt_dgrad(o.g, to.grad, to.dt, w, o.wdt, o.wpitch, ti.grad, o.acc_in, s));
+                }
                 prof_end(ph, s);
             }
             break;

@@ -3,6 +3,7 @@
 #include <string>
 #include <vector>
 #include "ops.cuh"
+#include "conv_umma.cuh"
 
 namespace b2 {
 
@@ -27,6 +28,10 @@ struct Op {
     uint8_t *idx;                // maxpool argmax
     int wdt, wpitch;             // conv: weight operand type / row pitch as the kernels see it
     bf16 *wcopy;                 // bf16 mode: compute copy of the weights [Co][wpitch]
+    bool use_umma;               // tcgen05 path (bf16, channel counts multiples of 64)
+    bf16 *wt;                    // tcgen05 dgrad operand: [Ci][taps*Co]
+    UmmaConvPlan fplan, dplan;
+    UmmaWgradPlan wplan;
 };
 
 // per-launch-group profiling (bench.py's roofline leg): CUDA events around every op
@@ -48,6 +53,9 @@ struct Model {
     void *slab = nullptr; size_t slab_bytes = 0;
     float *wgrad_ws = nullptr; size_t wgrad_floats = 0;
     bool weights_dirty = true;
+    bool plans_ready = false;
+    int conv_impl = 1;           // 0 = SIMT everywhere, 1 = tcgen05 where eligible
+    int build_plans();
     int64_t steps_tracked = 0;
     bool profiling = false;
     std::vector<ProfRec> prof;

@@ -104,6 +104,14 @@ int b2_model_num_ops(const b2_model *m);
 int b2_model_read_activation(b2_model *m, int op, int want_grad, float *out, int64_t capacity,
                              int64_t *numel, int shape[4], void *stream);
 
+/* kernel-level parity hook: ONE convolution pass on caller buffers (NHWC bf16 activations,
+ * fp32 O,H,W,I master weights) through the tcgen05 path (use_umma=1) or the CUDA-core path
+ * (use_umma=0).  mode 0: out = y bf16 [N,Ho,Wo,Co]; 1: out = dx bf16 [N,Hi,Wi,Ci] (acc: +=);
+ * 2: out = dw fp32 [Co][k*k*Ci].  Synchronises the stream. */
+int b2_conv_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, int pad, int mode,
+                 int use_umma, int acc, const void *x_bf16, const float *w_master,
+                 const void *dy_bf16, void *out, void *stream);
+
 /* ---- criterion: nn.CrossEntropyLoss() fwd+bwd (cifar_example_ddp.py:85,105) -- */
 int b2_ce_loss_grad(const float *logits, const int64_t *labels, int batch, int classes,
                     float *loss_out, float *dlogits, void *stream);
