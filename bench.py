@@ -212,10 +212,14 @@ def run_b2(args):
         sync_all()
         return ms, last
 
+    sampler = ClockSampler(dev) if (rank == 0 and not args.no_clocks) else None   # nvidia-smi needs ~1 s to start
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    if sampler is not None:
+        t_end = time.time() + 1.5
+        while time.time() < t_end:                           # keep the GPU under load until samples flow
+            step_resident()
     launches0 = b2.lib().b2_launch_count()
-    sampler = ClockSampler(dev) if rank == 0 else None
     ms, last = timed(step_resident, args.steps)
     launches = b2.lib().b2_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
@@ -290,6 +294,7 @@ def main():
     ap.add_argument("--impl", default="b2", choices=["b2", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="skip the nvidia-smi sampler (profiler runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

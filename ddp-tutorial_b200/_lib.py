@@ -39,13 +39,16 @@ _SIGS = {
     "b2_model_mark_weights_dirty": (_i, [_vp]),
     "b2_forward": (_i, [_vp, _vp, _vp, _vp]),
     "b2_backward": (_i, [_vp, _vp, _vp]),
+    "b2_model_set_graphs": (_i, [_vp, _i]),
     "b2_model_profile": (_i, [_vp, _i]),
     "b2_model_profile_collect": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i)]),
     "b2_model_num_ops": (_i, [_vp]),
     "b2_model_read_activation": (_i, [_vp, _i, _i, _vp, _i64, C.POINTER(_i64), C.POINTER(_i), _vp]),
     "b2_conv_test": (_i, [_i] * 11 + [_vp, _vp, _vp, _vp, _vp]),
     "b2_ce_loss_grad": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
-    "b2_sgd": (_i, [_vp, _vp, _vp, _i64, _f, _f, _f, _i, _vp]),
+    "b2_sgd": (_i, [_vp, _vp, _vp, _i64, _f, _f, _f, _i, _vp, _vp]),
+    "b2_model_bind_bf16": (_i, [_vp, _vp]),
+    "b2_model_mark_weights_clean": (_i, [_vp]),
     "b2_comm_init": (_i, [_i, _i, _i]),
     "b2_comm_finalize": (_i, []),
     "b2_comm_alloc": (_i, [_i64, C.POINTER(_vp)]),

@@ -79,6 +79,20 @@ int b2_model_bind(b2_model *h, float *params, float *grads, float *buffers) {
     h->m->p_params = params; h->m->p_grads = grads; h->m->p_buffers = buffers;
     h->m->weights_dirty = true;
     h->m->plans_ready = false;
+    h->m->drop_graphs();
+    return 0;
+}
+int b2_model_bind_bf16(b2_model *h, void *bf16_params) {
+    B2_CHECK(h, B2_ERR_ARG, "NULL model");
+    B2_CHECK(h->m->precision == B2_PREC_BF16, B2_ERR_STATE, "bind_bf16: model is not in bf16 mode");
+    B2_CHECK(((uintptr_t)bf16_params % 128) == 0, B2_ERR_ARG, "bind_bf16: mirror must be 128-byte aligned");
+    h->m->p_params_bf16 = bf16_params ? (bf16 *)bf16_params : h->m->own_bf16;
+    h->m->weights_dirty = true; h->m->plans_ready = false; h->m->drop_graphs();
+    return 0;
+}
+int b2_model_mark_weights_clean(b2_model *h) {
+    B2_CHECK(h, B2_ERR_ARG, "NULL model");
+    h->m->weights_dirty = false;
     return 0;
 }
 int b2_model_sync_weights(b2_model *h, void *stream) {
@@ -102,6 +116,12 @@ int b2_backward(b2_model *h, const float *dlogits, void *stream) {
 int b2_model_mark_weights_dirty(b2_model *h) {
     B2_CHECK(h, B2_ERR_ARG, "NULL model");
     h->m->weights_dirty = true;
+    return 0;
+}
+int b2_model_set_graphs(b2_model *h, int enable) {
+    B2_CHECK(h, B2_ERR_ARG, "NULL model");
+    h->m->use_graphs = enable != 0;
+    if (!enable) h->m->drop_graphs();
     return 0;
 }
 int b2_model_profile(b2_model *h, int enable) {
@@ -145,12 +165,12 @@ int b2_ce_loss_grad(const float *logits, const int64_t *labels, int batch, int c
 }
 
 int b2_sgd(float *p, const float *g, float *m, int64_t n, float lr, float momentum, float grad_scale, int first_step,
-           void *stream) {
+           void *p_bf16, void *stream) {
     GUARD_BEGIN
     B2_CHECK(n >= 0, B2_ERR_ARG, "b2_sgd: negative length");
     if (n == 0) return 0;
     B2_CHECK(p && g && m, B2_ERR_ARG, "b2_sgd: NULL argument");
-    return op_sgd(p, g, m, n, lr, momentum, grad_scale, first_step, (cudaStream_t)stream);
+    return op_sgd(p, g, m, n, lr, momentum, grad_scale, first_step, (bf16 *)p_bf16, (cudaStream_t)stream);
     GUARD_END
 }
 
@@ -166,15 +186,18 @@ int b2_conv_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, int p
     bf16 *w = nullptr, *wt = nullptr; float *ws = nullptr;
     size_t wsf = std::max(umma_wgrad_workspace(g), conv_simt_wgrad_workspace(g)) + 64;
     B2_CUDA(cudaMalloc(&w, (size_t)Co * taps * Ci * 2));
-    B2_CUDA(cudaMalloc(&wt, (size_t)Co * taps * Ci * 2));
     B2_CUDA(cudaMalloc(&ws, wsf * 4));
-    int rc = umma_prepare_weights(w_master, w, wt, Co, Ci, taps, s);
+    int rc = op_f32_to_bf16(w_master, w, (int64_t)Co * taps * Ci, s);
     if (rc == 0) {
         if (use_umma) {
             if (!umma_conv_eligible(g)) { set_error("conv_test: shape not eligible for the tcgen05 path"); rc = B2_ERR_UNSUPPORTED; }
             else if (mode == 0) { UmmaConvPlan pl; rc = umma_plan_fprop(g, (const bf16 *)x_bf16, w, (bf16 *)out, &pl); if (!rc) rc = umma_conv_launch(pl, s); }
-            else if (mode == 1) { UmmaConvPlan pl; rc = umma_plan_dgrad(g, (const bf16 *)dy_bf16, wt, (bf16 *)out, acc != 0, &pl); if (!rc) rc = umma_conv_launch(pl, s); }
-            else { UmmaWgradPlan pl; rc = umma_plan_wgrad(g, (const bf16 *)x_bf16, (const bf16 *)dy_bf16, (float *)out, ws, wsf, &pl); if (!rc) rc = umma_wgrad_launch(pl, s); }
+            else if (mode == 1) { UmmaConvPlan pl; rc = umma_plan_dgrad(g, (const bf16 *)dy_bf16, w, (bf16 *)out, acc != 0, &pl); if (!rc) rc = umma_conv_launch(pl, s); }
+            else {
+                UmmaWgradPlan pl; rc = umma_plan_wgrad(g, (const bf16 *)x_bf16, (const bf16 *)dy_bf16, (float *)out, ws, wsf, &pl);
+                if (!rc) rc = umma_wgrad_zero_dead(pl, s);
+                if (!rc) rc = umma_wgrad_launch(pl, s);
+            }
         } else {
             if (mode == 0) rc = conv_simt_fprop(g, x_bf16, DT_BF16, w, DT_BF16, g.K(), nullptr, false, out, DT_BF16, s);
             else if (mode == 1) rc = conv_simt_dgrad(g, dy_bf16, DT_BF16, w, DT_BF16, g.K(), out, acc != 0, s);

@@ -144,13 +144,15 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
                 mbar_arrive_expect_tx(&full[stage], kATileBytes + kBTileBytes);
                 tma_load_4d(sA + stage * kATileBytes, &a_map, &full[stage], cc * 64, cls.dw[tap],
                             h_blk * p.BH * p.a_hstep + cls.dh[tap], n_blk * p.BN);
-                tma_load_2d(sB + stage * kBTileBytes, &b_map, &full[stage], cls.kofs[tap] + cc * 64, ch0);
+                if (p.b_mn) tma_load_2d(sB + stage * kBTileBytes, &b_map, &full[stage], cls.kofs[tap] + ch0, cc * 64);
+                else tma_load_2d(sB + stage * kBTileBytes, &b_map, &full[stage], cls.kofs[tap] + cc * 64, ch0);
                 if (++stage == kStagesTap) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+            const uint32_t idesc = make_idesc_bf16(128, 64, 0, p.b_mn);
+            const uint32_t bstep = p.b_mn ? 2048 : 32;     // 16 K-rows of 128 B vs 16 K-elements
             int stage = 0; uint32_t phase = 0;
             for (int ks = 0; ks < ksteps; ++ks) {
                 mbar_wait(&full[stage], phase);
@@ -158,8 +160,8 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
                 const uint32_t a0 = smem_u32(sA + stage * kATileBytes), b0 = smem_u32(sB + stage * kBTileBytes);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    mma_bf16_ss(tmem_base, make_desc_sw128(a0 + k * 32, 16, 1024), make_desc_sw128(b0 + k * 32, 16, 1024),
-                                idesc, (ks | k) != 0);
+                    mma_bf16_ss(tmem_base, make_desc_sw128(a0 + k * 32, 16, 1024),
+                                make_desc_sw128(b0 + k * bstep, kBTileBytes, 1024), idesc, (ks | k) != 0);
                 }
                 mma_commit(&empty[stage]);
                 if (++stage == kStagesTap) { stage = 0; phase ^= 1; }
@@ -291,12 +293,12 @@ k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUten
         else { row = q * 16 + lane; valid = lane < 16; }
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        float *dst_row = p.out + ((int64_t)blockIdx.z * p.Co + co0 + row) * p.K;
+        float *dst_row = p.out + ((int64_t)blockIdx.z * p.Co + co0 + row) * p.out_pitch;
         uint32_t v[32];
         for (int j = 0; j < nb; ++j) {
             const int c = chunk0 + j;
             const int tap = c / p.c_chunks, cc = c - tap * p.c_chunks;
-            float *dst = dst_row + (int64_t)p.tap_id[tap] * p.Ci + cc * 64;
+            float *dst = dst_row + (p.compact ? (int64_t)c * 64 : (int64_t)p.tap_id[tap] * p.Ci + cc * 64);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + j * 64 + half * 32, v);
@@ -350,7 +352,7 @@ int umma_plan_fprop(const ConvGeom &g, const bf16 *x, const bf16 *w, bf16 *y, Um
     return 0;
 }
 
-int umma_plan_dgrad(const ConvGeom &g, const bf16 *dy, const bf16 *wt, bf16 *dx, bool acc, UmmaConvPlan *plan) {
+int umma_plan_dgrad(const ConvGeom &g, const bf16 *dy, const bf16 *w, bf16 *dx, bool acc, UmmaConvPlan *plan) {
     plan->valid = false;
     B2_CHECK(umma_conv_eligible(g), B2_ERR_UNSUPPORTED, "umma dgrad: shape not eligible");
     TapGemmParams &p = plan->p;
@@ -359,6 +361,7 @@ int umma_plan_dgrad(const ConvGeom &g, const bf16 *dy, const bf16 *wt, bf16 *dx,
     B2_CHECK(tile_geometry(g.N, g.Ho, g.Wo, &p.BW, &p.BH, &p.BN), B2_ERR_UNSUPPORTED, "umma dgrad: tile geometry");
     p.h_blocks = g.Ho / p.BH; p.a_hstep = 1; p.c_chunks = g.Co / 64;
     p.out_H = g.Hi; p.out_W = g.Wi; p.out_C = g.Ci; p.os = g.stride; p.out = dx; p.acc = acc ? 1 : 0; p.stats = nullptr;
+    p.b_mn = 1;
     const int s = g.stride;
     p.nclasses = 0;
     double taps_total = 0;
@@ -373,14 +376,14 @@ int umma_plan_dgrad(const ConvGeom &g, const bf16 *dy, const bf16 *wt, bf16 *dx,
                     if (((th % s) + s) % s != 0 || ((tw % s) + s) % s != 0) continue;
                     int dh = th >= 0 ? th / s : -((-th) / s), dw = tw >= 0 ? tw / s : -((-tw) / s);
                     if (!tap_alive(dh, 1, g.Ho, g.Ho) || !tap_alive(dw, 1, g.Wo, g.Wo)) continue;
-                    c.dh[c.ntaps] = dh; c.dw[c.ntaps] = dw; c.kofs[c.ntaps] = (kh * g.kw + kw) * g.Co; ++c.ntaps;
+                    c.dh[c.ntaps] = dh; c.dw[c.ntaps] = dw; c.kofs[c.ntaps] = (kh * g.kw + kw) * g.Ci; ++c.ntaps;
                 }
             taps_total += c.ntaps;
             if (c.ntaps > 0) ++p.nclasses;      // a class without taps contributes nothing
             else B2_CHECK(acc || s == 1, B2_ERR_UNSUPPORTED, "umma dgrad: empty parity class needs acc (caller zero-fills)");
         }
     B2_TRY(make_map_nhwc(&plan->a_map, dy, g.N, g.Ho, g.Wo, g.Co, p.BW, p.BH, p.BN, 1));
-    B2_TRY(make_map_2d(&plan->b_map, wt, g.Ci, (int64_t)g.kh * g.kw * g.Co, 64));
+    B2_TRY(make_map_2d(&plan->b_map, w, g.Co, (int64_t)g.kh * g.kw * g.Ci, 64));
     plan->grid = dim3((unsigned)(g.N / p.BN * p.h_blocks), (unsigned)(g.Ci / 64), (unsigned)p.nclasses);
     plan->flops = 2.0 * (double)g.N * g.Ho * g.Wo * g.Ci * taps_total * g.Co;
     plan->valid = true;
@@ -418,7 +421,7 @@ static void wgrad_shape(const ConvGeom &g, int *ntaps_alive, int *m_boxes, int *
 size_t umma_wgrad_workspace(const ConvGeom &g) {
     int a, mb, kt, pt, sp, per;
     wgrad_shape(g, &a, &mb, &kt, &pt, &sp, &per);
-    return sp > 1 ? (size_t)sp * g.Co * g.K() : 0;
+    return sp > 1 ? (size_t)sp * g.Co * a * g.Ci : 0;
 }
 
 int umma_plan_wgrad(const ConvGeom &g, const bf16 *x, const bf16 *dy, float *dw, float *partial, size_t partial_floats,
@@ -440,9 +443,9 @@ int umma_plan_wgrad(const ConvGeom &g, const bf16 *x, const bf16 *dy, float *dw,
     plan->need_zero = n < g.kh * g.kw;
     plan->dw = dw;
     if (p.splits > 1) {
-        B2_CHECK((size_t)p.splits * g.Co * g.K() <= partial_floats, B2_ERR_ARG, "umma wgrad: workspace too small");
-        p.out = partial;
-    } else p.out = dw;
+        B2_CHECK((size_t)p.splits * g.Co * n * g.Ci <= partial_floats, B2_ERR_ARG, "umma wgrad: workspace too small");
+        p.out = partial; p.out_pitch = n * g.Ci; p.compact = 1;
+    } else { p.out = dw; p.out_pitch = g.K(); p.compact = 0; }
     B2_TRY(make_map_nhwc(&plan->x_map, x, g.N, g.Hi, g.Wi, g.Ci, p.BW, p.BH, p.BN, g.stride));
     B2_TRY(make_map_2d(&plan->dy_map, dy, g.M(), g.Co, 128));
     plan->grid = dim3((unsigned)kt, (unsigned)(g.Co / (64 * p.m_boxes)), (unsigned)p.splits);
@@ -451,21 +454,26 @@ int umma_plan_wgrad(const ConvGeom &g, const bf16 *x, const bf16 *dy, float *dw,
     return 0;
 }
 
-__global__ void k_reduce_partials2(const float *__restrict__ part, float *__restrict__ out, int64_t n, int splits) {
-    int64_t n4 = n >> 2;
+// dW[co][tap_id*Ci + c] = sum_z partial[z][co][a*Ci + c]   (a = live-tap index), float4 lanes
+__global__ void k_wgrad_reduce(const float *__restrict__ part, float *__restrict__ dw, WgradParams p) {
+    const int akc = p.out_pitch;                 // live taps * Ci
+    const int64_t per_split = (int64_t)p.Co * akc;
+    const int64_t n4 = per_split >> 2;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 s = ((const float4 *)part)[i];
-        for (int z = 1; z < splits; ++z) {
-            float4 v = ((const float4 *)(part + (int64_t)z * n))[i];
+        for (int z = 1; z < p.splits; ++z) {
+            float4 v = ((const float4 *)(part + (int64_t)z * per_split))[i];
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
-        ((float4 *)out)[i] = s;
+        const int64_t e = i << 2;
+        const int co = (int)(e / akc); const int col = (int)(e - (int64_t)co * akc);
+        const int a = col / p.Ci; const int c = col - a * p.Ci;
+        *(float4 *)(dw + (int64_t)co * p.K + (int64_t)p.tap_id[a] * p.Ci + c) = s;
     }
 }
-int reduce_partials(const float *part, float *out, int64_t n, int splits, cudaStream_t s) {
-    B2_CHECK(n % 4 == 0, B2_ERR_ARG, "reduce_partials: n must be a multiple of 4");
-    int blocks = (int)ceil_div(n / 4, 256); if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    B2_LAUNCH(k_reduce_partials2, blocks, 256, 0, s, part, out, n, splits);
+
+int umma_wgrad_zero_dead(const UmmaWgradPlan &plan, cudaStream_t s) {
+    if (plan.need_zero) B2_CUDA(cudaMemsetAsync(plan.dw, 0, (size_t)plan.p.Co * plan.p.K * 4, s));
     return 0;
 }
 
@@ -473,32 +481,14 @@ int umma_wgrad_launch(const UmmaWgradPlan &plan, cudaStream_t s) {
     B2_CHECK(plan.valid, B2_ERR_STATE, "umma wgrad: plan not valid");
     std::call_once(g_attr_once, set_attrs);
     const WgradParams &p = plan.p;
-    const int64_t n = (int64_t)p.Co * p.K;
-    if (plan.need_zero) B2_CUDA(cudaMemsetAsync(p.out, 0, (size_t)n * 4 * p.splits, s));
     k_wgrad<<<plan.grid, 192, kWgSmem, s>>>(plan.x_map, plan.dy_map, plan.p);
     ++g_launches;
     B2_CUDA(cudaGetLastError());
-    if (p.splits > 1) B2_TRY(reduce_partials(p.out, plan.dw, n, p.splits, s));
-    return 0;
-}
-
-// fp32 master (O,H,W,I) -> bf16 w [Co][taps*Ci] and wt [Ci][taps*Co]
-__global__ void k_prepare_weights(const float *__restrict__ m, bf16 *__restrict__ w, bf16 *__restrict__ wt, int Co, int Ci, int taps) {
-    int64_t total = (int64_t)Co * taps * Ci;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        bf16 v = __float2bfloat16_rn(m[i]);
-        w[i] = v;
-        if (wt) {
-            int ci = i % Ci; int64_t r = i / Ci;
-            int tap = r % taps; int co = (int)(r / taps);
-            wt[((int64_t)ci * taps + tap) * Co + co] = v;
-        }
+    if (p.splits > 1) {
+        int64_t n4 = (int64_t)p.Co * p.out_pitch / 4;
+        int blocks = (int)ceil_div(n4, 256); if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        B2_LAUNCH(k_wgrad_reduce, blocks, 256, 0, s, p.out, plan.dw, p);
     }
-}
-int umma_prepare_weights(const float *master, bf16 *w, bf16 *wt, int Co, int Ci, int taps, cudaStream_t s) {
-    int64_t total = (int64_t)Co * taps * Ci;
-    int blocks = (int)ceil_div(total, 256); if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    B2_LAUNCH(k_prepare_weights, blocks, 256, 0, s, master, w, wt, Co, Ci, taps);
     return 0;
 }
 

@@ -25,6 +25,9 @@ struct TapGemmParams {
     int out_H, out_W, out_C, os;
     bf16 *out;
     int acc;                    // 1: out += result (bf16 read-modify-write)
+    int b_mn;                   // 0: B tile rows = output channel, cols = K (fprop)
+                                // 1: B tile rows = K (co), cols = output channel (dgrad reads the
+                                //    same [Co][taps*Ci] weight copy as an MN-major operand)
     float *stats;               // optional [2][out_C] per-channel sum / sum of squares (atomics); may be null
 };
 
@@ -44,7 +47,9 @@ struct WgradParams {
     int BW, BH, BN, h_blocks, a_hstep;
     int pix_tiles, tiles_per_split, splits;
     int m_boxes;                // Co tile = 64*m_boxes (1 or 2)
-    float *out;                 // dW (splits == 1) or partial buffer [splits][Co][K]
+    float *out;                 // dW (splits == 1) or compact partials [splits][Co][alive taps*Ci]
+    int out_pitch;              // row pitch of `out` in floats
+    int compact;                // 1: columns are (alive tap, ci); 0: columns are (tap id, ci) as in dW
 };
 
 struct UmmaWgradPlan {
@@ -60,16 +65,13 @@ struct UmmaWgradPlan {
 bool umma_conv_eligible(const ConvGeom &g);
 int umma_init();   // resolves the driver entry point for tensor-map encoding
 int umma_plan_fprop(const ConvGeom &g, const bf16 *x, const bf16 *w, bf16 *y, UmmaConvPlan *plan);
-int umma_plan_dgrad(const ConvGeom &g, const bf16 *dy, const bf16 *wt, bf16 *dx, bool acc, UmmaConvPlan *plan);
+int umma_plan_dgrad(const ConvGeom &g, const bf16 *dy, const bf16 *w, bf16 *dx, bool acc, UmmaConvPlan *plan);
 int umma_conv_launch(const UmmaConvPlan &plan, cudaStream_t s);
 size_t umma_wgrad_workspace(const ConvGeom &g);
 int umma_plan_wgrad(const ConvGeom &g, const bf16 *x, const bf16 *dy, float *dw, float *partial, size_t partial_floats,
                     UmmaWgradPlan *plan);
 int umma_wgrad_launch(const UmmaWgradPlan &plan, cudaStream_t s);
-// bf16 compute copies of a conv weight from the fp32 master (O,H,W,I):
-//   w  [Co][taps*Ci]   (fprop B operand, K = (tap, ci))
-//   wt [Ci][taps*Co]   (dgrad B operand, K = (tap, co))
-int umma_prepare_weights(const float *master, bf16 *w, bf16 *wt, int Co, int Ci, int taps, cudaStream_t s);
-int reduce_partials(const float *part, float *out, int64_t n, int splits, cudaStream_t s);
+// zero the dW columns of taps that never touch the input (call once; they are never written)
+int umma_wgrad_zero_dead(const UmmaWgradPlan &plan, cudaStream_t s);
 
 }  // namespace b2

@@ -29,7 +29,7 @@ int64_t Model::add_param(const std::string &name, int rank, const int64_t *shape
     p.name = name; p.rank = rank; p.numel = numel;
     for (int i = 0; i < 4; ++i) { p.shape[i] = i < rank ? shape[i] : 1; p.stride[i] = i < rank ? stride[i] : 0; }
     p.offset = n_params;
-    n_params += (numel + 3) / 4 * 4;     // keep every tensor 16-byte aligned in the flat vector
+    n_params += (numel + 63) / 64 * 64;  // every tensor starts 128-byte aligned in the bf16 mirror (TMA base)
     params.push_back(p);
     return p.offset;
 }
@@ -216,7 +216,7 @@ int Model::finalize() {
         voff[i] = reserve(t.numel * dt_size(t.dt));
         goff[i] = reserve(t.numel * dt_size(t.dt));
     }
-    struct Scratch { size_t partial, mean, invstd, coef, idx, wcopy, wt; };
+    struct Scratch { size_t partial, mean, invstd, coef, idx, col, wpad, dwpad; };
     std::vector<Scratch> so(ops.size());
     size_t wg_floats = 0;
     for (size_t i = 0; i < ops.size(); ++i) {
@@ -232,18 +232,30 @@ int Model::finalize() {
         } else if (o.type == OP_CONV) {
             wg_floats = std::max(wg_floats, conv_simt_wgrad_workspace(o.g));
             o.wdt = DT_F32; o.wpitch = o.g.K();
-            if (tensors[o.in].dt == DT_BF16) {
-                o.wdt = DT_BF16; o.wpitch = (o.g.K() + 63) / 64 * 64;
-                so[i].wcopy = reserve((size_t)o.g.Co * o.wpitch * 2);
-                o.use_umma = conv_impl == 1 && tensors[o.out].dt == DT_BF16 && !o.relu && o.b_off < 0 && umma_conv_eligible(o.g);
-                if (o.use_umma) {
-                    so[i].wt = reserve((size_t)o.g.Ci * o.g.kh * o.g.kw * o.g.Co * 2);
-                    wg_floats = std::max(wg_floats, umma_wgrad_workspace(o.g));
+            o.is_fc = tensors[o.in].dt == DT_F32 && tensors[o.out].dt == DT_F32 && o.g.kh == 1 && o.g.Hi == 1 && o.g.Wi == 1 &&
+                      o.g.stride == 1 && o.g.pad == 0 && o.g.Co <= 32 && kind != B2_MODEL_NET;
+            if (tensors[o.in].dt == DT_BF16 && o.in == input_tensor && conv_impl == 1 && !o.relu && o.b_off < 0 && o.g.Co % 64 == 0) {
+                o.kpad = (o.g.K() + 63) / 64 * 64;
+                ConvGeom v{};
+                v.N = o.g.N; v.Hi = v.Ho = o.g.Ho; v.Wi = v.Wo = o.g.Wo; v.Ci = o.kpad; v.Co = o.g.Co;
+                v.kh = v.kw = 1; v.stride = 1; v.pad = 0;
+                if (umma_conv_eligible(v)) {
+                    o.stem_umma = true; o.vg = v; o.wdt = DT_BF16;
+                    so[i].col = reserve((size_t)v.M() * o.kpad * 2);
+                    so[i].wpad = reserve((size_t)v.Co * o.kpad * 2);
+                    so[i].dwpad = reserve((size_t)v.Co * o.kpad * 4);
+                    wg_floats = std::max(wg_floats, umma_wgrad_workspace(v));
                 }
+            }
+            if (!o.stem_umma && tensors[o.in].dt == DT_BF16) {
+                o.wdt = DT_BF16;
+                o.use_umma = conv_impl == 1 && tensors[o.out].dt == DT_BF16 && !o.relu && o.b_off < 0 && umma_conv_eligible(o.g);
+                if (o.use_umma) wg_floats = std::max(wg_floats, umma_wgrad_workspace(o.g));
             }
         }
     }
     size_t wg_off = reserve(wg_floats * 4 + 256);
+    size_t bf_off = precision == B2_PREC_BF16 ? reserve((size_t)n_params * 2 + 256) : 0;
     wgrad_floats = wg_floats;
     B2_CUDA(cudaMalloc(&slab, total));
     B2_CUDA(cudaMemset(slab, 0, total));
@@ -257,12 +269,12 @@ int Model::finalize() {
             o.bn.invstd = (float *)(base + so[i].invstd); o.bn.coef = (float *)(base + so[i].coef);
         } else if (o.type == OP_MAXPOOL) {
             o.idx = (uint8_t *)(base + so[i].idx);
-        } else if (o.type == OP_CONV && o.wdt == DT_BF16) {
-            o.wcopy = (bf16 *)(base + so[i].wcopy);
-            if (o.use_umma) o.wt = (bf16 *)(base + so[i].wt);
+        } else if (o.type == OP_CONV && o.stem_umma) {
+            o.col = (bf16 *)(base + so[i].col); o.wpad = (bf16 *)(base + so[i].wpad); o.dwpad = (float *)(base + so[i].dwpad);
         }
     }
     wgrad_ws = (float *)(base + wg_off);
+    if (precision == B2_PREC_BF16) { own_bf16 = (bf16 *)(base + bf_off); p_params_bf16 = own_bf16; }
     return 0;
 }
 
@@ -274,6 +286,8 @@ bool Model::ops_produce(int tensor) const {
 }
 
 Model::~Model() {
+    drop_graphs();
+    if (cap_stream) cudaStreamDestroy(cap_stream);
     if (slab) cudaFree(slab);
 }
 
@@ -310,42 +324,97 @@ int Model::prof_collect(double ms[PC_COUNT], double flops[PC_COUNT], double byte
 // =================================================================================
 int Model::sync_weights(cudaStream_t s) {
     B2_CHECK(p_params, B2_ERR_STATE, "model: parameters not bound");
-    for (Op &o : ops)
-        if (o.type == OP_CONV && o.wdt == DT_BF16) {
-            if (o.use_umma)
-                B2_TRY(umma_prepare_weights(p_params + o.w_off, o.wcopy, o.need_dgrad ? o.wt : nullptr, o.g.Co, o.g.Ci,
-                                            o.g.kh * o.g.kw, s));
-            else
-                B2_TRY(op_f32_to_bf16_padded(p_params + o.w_off, o.wcopy, o.g.Co, o.g.K(), o.wpitch, s));
-        }
+    if (p_params_bf16) B2_TRY(op_f32_to_bf16(p_params, p_params_bf16, n_params, s));
     weights_dirty = false;
     return 0;
 }
 
 int Model::build_plans() {
     for (Op &o : ops) {
+        if (o.type == OP_CONV && o.stem_umma) {
+            Tensor &to = tensors[o.out];
+            B2_TRY(umma_plan_fprop(o.vg, o.col, o.wpad, (bf16 *)to.val, &o.fplan));
+            B2_TRY(umma_plan_wgrad(o.vg, o.col, (const bf16 *)to.grad, o.dwpad, wgrad_ws, wgrad_floats, &o.wplan));
+            continue;
+        }
         if (o.type != OP_CONV || !o.use_umma) continue;
         Tensor &ti = tensors[o.in], &to = tensors[o.out];
-        B2_TRY(umma_plan_fprop(o.g, (const bf16 *)ti.val, o.wcopy, (bf16 *)to.val, &o.fplan));
+        const bf16 *wb = p_params_bf16 + o.w_off;
+        B2_TRY(umma_plan_fprop(o.g, (const bf16 *)ti.val, wb, (bf16 *)to.val, &o.fplan));
         if (o.need_dgrad) {
             // a 1x1 stride-2 dgrad only touches even pixels: zero-fill first when it is the first writer
             bool sparse = o.g.stride == 2 && o.g.kh == 1;
-            B2_TRY(umma_plan_dgrad(o.g, (const bf16 *)to.grad, o.wt, (bf16 *)ti.grad, o.acc_in || sparse, &o.dplan));
+            B2_TRY(umma_plan_dgrad(o.g, (const bf16 *)to.grad, wb, (bf16 *)ti.grad, o.acc_in || sparse, &o.dplan));
         }
         B2_TRY(umma_plan_wgrad(o.g, (const bf16 *)ti.val, (const bf16 *)to.grad, p_grads + o.w_off, wgrad_ws, wgrad_floats, &o.wplan));
+        B2_TRY(umma_wgrad_zero_dead(o.wplan, 0));      // once: dead-tap gradients are exactly zero and never rewritten
     }
+    B2_CUDA(cudaStreamSynchronize(0));
     plans_ready = true;
+    return 0;
+}
+
+void Model::drop_graphs() {
+    for (auto &g : fwd_graphs) cudaGraphExecDestroy(g.exec);
+    for (auto &g : bwd_graphs) cudaGraphExecDestroy(g.exec);
+    fwd_graphs.clear(); bwd_graphs.clear();
+}
+
+int Model::run_graphed(std::vector<GraphEntry> &cache, const void *a, const void *b, bool is_fwd, cudaStream_t s) {
+    for (GraphEntry &g : cache)
+        if (g.a == a && g.b == b) {
+            B2_CUDA(cudaGraphLaunch(g.exec, s));
+            g_launches += g.launches;
+            return 0;
+        }
+    if (!cap_stream) B2_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+    if (cache.size() >= 8) { cudaGraphExecDestroy(cache.front().exec); cache.erase(cache.begin()); }
+    const int64_t l0 = g_launches;
+    B2_CUDA(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = is_fwd ? forward_impl((const float *)a, (float *)const_cast<void *>(b), cap_stream)
+                    : backward_impl((const float *)a, cap_stream);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(cap_stream, &graph);
+    const int64_t captured = g_launches - l0;
+    g_launches = l0;
+    if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
+    cache.push_back(GraphEntry{a, b, exec, captured});
+    B2_CUDA(cudaGraphLaunch(exec, s));
+    g_launches += captured;
     return 0;
 }
 
 int Model::forward(const float *x_nchw, float *logits, cudaStream_t s) {
     B2_CHECK(p_params && p_grads, B2_ERR_STATE, "model: parameters/gradients not bound (b2_model_bind)");
     if (!plans_ready) B2_TRY(build_plans());
-    if (weights_dirty) B2_TRY(sync_weights(s));
+    // the first two calls run eagerly (lazy module loading, function attributes), then replay
+    if (weights_dirty) B2_TRY(sync_weights(s));        // never inside a graph: depends on host state
+    if (use_graphs && !profiling && eager_runs_fwd >= 2) {
+        B2_TRY(run_graphed(fwd_graphs, x_nchw, logits, true, s));
+        ++steps_tracked;
+        return 0;
+    }
+    ++eager_runs_fwd;
+    B2_TRY(forward_impl(x_nchw, logits, s));
+    ++steps_tracked;
+    return 0;
+}
+
+int Model::forward_impl(const float *x_nchw, float *logits, cudaStream_t s) {
+    cur_x = x_nchw;
+
     for (Op &o : ops) {
         Tensor &to = tensors[o.out];
         switch (o.type) {
         case OP_INPUT: {
+            bool needed = false;
+            for (const Op &c : ops) if ((c.in == o.out || c.res == o.out) && !(c.type == OP_CONV && c.stem_umma)) needed = true;
+            if (!needed) break;
             int ph = prof_begin(PC_OTHER, 0, to.numel * (4.0 + dt_size(to.dt)), s);
             B2_TRY(op_nchw_to_nhwc(x_nchw, to.val, to.dt, to.N, to.C, to.H, to.W, s));
             prof_end(ph, s);
@@ -353,7 +422,24 @@ int Model::forward(const float *x_nchw, float *logits, cudaStream_t s) {
         }
         case OP_CONV: {
             Tensor &ti = tensors[o.in];
-            const void *w = o.wdt == DT_BF16 ? (const void *)o.wcopy : (const void *)(p_params + o.w_off);
+            if (o.stem_umma) {
+                int ph = prof_begin(PC_CONV_FPROP, 2.0 * o.g.M() * o.g.Co * o.g.K(), (double)o.vg.M() * o.kpad * 4 + to.numel * 2.0, s);
+                B2_TRY(op_stem_im2col(cur_x, o.col, o.g.N, o.g.Ci, o.g.Hi, o.g.Wi, o.g.kh, o.g.stride, o.g.pad, o.g.Ho, o.g.Wo, o.kpad, s));
+                B2_TRY(op_f32_to_bf16_padded(p_params + o.w_off, o.wpad, o.g.Co, o.g.K(), o.kpad, s));
+                B2_TRY(umma_conv_launch(o.fplan, s));
+                prof_end(ph, s);
+                break;
+            }
+            if (o.is_fc) {
+                int ph = prof_begin(PC_OTHER, 0, 0, s);
+                B2_TRY(op_fc_forward((const float *)ti.val, p_params + o.w_off, o.b_off >= 0 ? p_params + o.b_off : nullptr,
+                                     (float *)to.val, o.g.N, o.g.Ci, o.g.Co, o.relu, s));
+                prof_end(ph, s);
+                if (o.out == logits_tensor && logits)
+                    B2_CUDA(cudaMemcpyAsync(logits, to.val, to.numel * 4, cudaMemcpyDeviceToDevice, s));
+                break;
+            }
+            const void *w = o.wdt == DT_BF16 ? (const void *)(p_params_bf16 + o.w_off) : (const void *)(p_params + o.w_off);
             const float *bias = o.b_off >= 0 ? p_params + o.b_off : nullptr;
             int ph = prof_begin(PC_CONV_FPROP, o.use_umma ? o.fplan.flops : 2.0 * o.g.M() * o.g.Co * o.g.K(),
                                 ti.numel * (double)dt_size(ti.dt) + to.numel * (double)dt_size(to.dt) + (double)o.g.Co * o.g.K() * dt_size(o.wdt), s);
@@ -377,8 +463,12 @@ int Model::forward(const float *x_nchw, float *logits, cudaStream_t s) {
         case OP_MAXPOOL: {
             Tensor &ti = tensors[o.in];
             int ph = prof_begin(PC_POOL, 0, (ti.numel + to.numel) * (double)dt_size(ti.dt) + to.numel, s);
-            B2_TRY(op_maxpool_forward(ti.val, to.val, o.idx, ti.dt, o.g.N, o.g.Hi, o.g.Wi, o.g.Ci, o.g.kh, o.g.stride,
-                                      o.g.pad, o.g.Ho, o.g.Wo, o.out_nchw, s));
+            if (ti.dt == DT_BF16 && !o.out_nchw && o.g.Ci % 8 == 0)
+                B2_TRY(op_maxpool_forward_bf16x8((const bf16 *)ti.val, (bf16 *)to.val, o.idx, o.g.N, o.g.Hi, o.g.Wi, o.g.Ci, o.g.kh,
+                                                 o.g.stride, o.g.pad, o.g.Ho, o.g.Wo, s));
+            else
+                B2_TRY(op_maxpool_forward(ti.val, to.val, o.idx, ti.dt, o.g.N, o.g.Hi, o.g.Wi, o.g.Ci, o.g.kh, o.g.stride,
+                                          o.g.pad, o.g.Ho, o.g.Wo, o.out_nchw, s));
             prof_end(ph, s);
             break;
         }
@@ -389,12 +479,17 @@ int Model::forward(const float *x_nchw, float *logits, cudaStream_t s) {
         }
         }
     }
-    ++steps_tracked;
     return 0;
 }
 
 int Model::backward(const float *dlogits, cudaStream_t s) {
     B2_CHECK(p_params && p_grads, B2_ERR_STATE, "model: parameters/gradients not bound (b2_model_bind)");
+    if (use_graphs && !profiling && eager_runs_bwd >= 2) return run_graphed(bwd_graphs, dlogits, nullptr, false, s);
+    ++eager_runs_bwd;
+    return backward_impl(dlogits, s);
+}
+
+int Model::backward_impl(const float *dlogits, cudaStream_t s) {
     Tensor &tl = tensors[logits_tensor];
     B2_CUDA(cudaMemcpyAsync(tl.grad, dlogits, tl.numel * 4, cudaMemcpyDeviceToDevice, s));
     for (int i = (int)ops.size() - 1; i >= 0; --i) {
@@ -404,7 +499,22 @@ int Model::backward(const float *dlogits, cudaStream_t s) {
         Tensor &ti = tensors[o.in];
         switch (o.type) {
         case OP_CONV: {
+            if (o.stem_umma) {
+                int ph = prof_begin(PC_CONV_WGRAD, 2.0 * o.g.M() * o.g.Co * o.g.K(), (double)o.vg.M() * o.kpad * 2 + to.numel * 2.0, s);
+                B2_TRY(umma_wgrad_launch(o.wplan, s));
+                B2_TRY(op_copy_2d_f32(o.dwpad, o.kpad, p_grads + o.w_off, o.g.K(), o.g.Co, o.g.K(), s));
+                prof_end(ph, s);
+                break;
+            }
             if (o.relu) B2_TRY(op_relu_mask(to.val, to.grad, to.dt, to.numel, s));
+            if (o.is_fc) {
+                int ph = prof_begin(PC_OTHER, 0, 0, s);
+                B2_TRY(op_fc_backward((const float *)ti.val, p_params + o.w_off, (const float *)to.grad, p_grads + o.w_off,
+                                      o.b_off >= 0 ? p_grads + o.b_off : nullptr, o.need_dgrad ? (float *)ti.grad : nullptr,
+                                      o.g.N, o.g.Ci, o.g.Co, o.acc_in, s));
+                prof_end(ph, s);
+                break;
+            }
             if (o.b_off >= 0) B2_TRY(op_bias_grad(to.grad, to.dt, o.g.M(), o.g.Co, p_grads + o.b_off, s));
             B2_CHECK(to.dt == ti.dt, B2_ERR_STATE, "conv backward: mixed activation types");
             const double cflops = 2.0 * o.g.M() * o.g.Co * o.g.K();
@@ -414,7 +524,7 @@ int Model::backward(const float *dlogits, cudaStream_t s) {
             else B2_TRY(conv_simt_wgrad(o.g, ti.val, to.grad, ti.dt, p_grads + o.w_off, wgrad_ws, wgrad_floats, s));
             prof_end(ph, s);
             if (o.need_dgrad) {
-                const void *w = o.wdt == DT_BF16 ? (const void *)o.wcopy : (const void *)(p_params + o.w_off);
+                const void *w = o.wdt == DT_BF16 ? (const void *)(p_params_bf16 + o.w_off) : (const void *)(p_params + o.w_off);
                 ph = prof_begin(PC_CONV_DGRAD, o.use_umma ? o.dplan.flops : cflops, cbytes + (double)o.g.Co * o.g.K() * dt_size(o.wdt), s);
                 if (o.use_umma) {
                     if (o.g.stride == 2 && o.g.kh == 1 && !o.acc_in)
@@ -437,9 +547,14 @@ int Model::backward(const float *dlogits, cudaStream_t s) {
             break;
         }
         case OP_MAXPOOL:
-            if (o.need_dgrad)
-                B2_TRY(op_maxpool_backward(to.grad, o.idx, ti.grad, ti.dt, o.g.N, o.g.Hi, o.g.Wi, o.g.Ci, o.g.kh,
-                                           o.g.stride, o.g.pad, o.g.Ho, o.g.Wo, o.out_nchw, o.acc_in, s));
+            if (o.need_dgrad) {
+                if (ti.dt == DT_BF16 && !o.out_nchw && o.g.Ci % 8 == 0)
+                    B2_TRY(op_maxpool_backward_bf16x8((const bf16 *)to.grad, o.idx, (bf16 *)ti.grad, o.g.N, o.g.Hi, o.g.Wi, o.g.Ci,
+                                                      o.g.kh, o.g.stride, o.g.pad, o.g.Ho, o.g.Wo, o.acc_in, s));
+                else
+                    B2_TRY(op_maxpool_backward(to.grad, o.idx, ti.grad, ti.dt, o.g.N, o.g.Hi, o.g.Wi, o.g.Ci, o.g.kh,
+                                               o.g.stride, o.g.pad, o.g.Ho, o.g.Wo, o.out_nchw, o.acc_in, s));
+            }
             break;
         case OP_AVGPOOL:
             B2_TRY(op_avgpool_backward((const float *)to.grad, ti.grad, ti.dt, ti.N, ti.H * ti.W, ti.C, o.acc_in, s));

@@ -27,9 +27,14 @@ struct Op {
     BnWork bn;
     uint8_t *idx;                // maxpool argmax
     int wdt, wpitch;             // conv: weight operand type / row pitch as the kernels see it
-    bf16 *wcopy;                 // bf16 mode: compute copy of the weights [Co][wpitch]
     bool use_umma;               // tcgen05 path (bf16, channel counts multiples of 64)
-    bf16 *wt;                    // tcgen05 dgrad operand: [Ci][taps*Co]
+    bool is_fc;                  // small fp32 classifier head -> dedicated kernels
+    // stem (Ci = 3): bf16 im2col rows + 1x1 tcgen05 GEMM over them
+    bool stem_umma;
+    ConvGeom vg;                 // the virtual 1x1 conv over the im2col tensor [N,Ho,Wo,kpad]
+    int kpad;
+    bf16 *col, *wpad;            // [M][kpad], [Co][kpad]
+    float *dwpad;                // [Co][kpad]
     UmmaConvPlan fplan, dplan;
     UmmaWgradPlan wplan;
 };
@@ -49,13 +54,27 @@ struct Model {
     std::vector<BufferInfo> buffers;
     int64_t n_params = 0, n_buffers = 0;
     int input_tensor = -1, logits_tensor = -1;
+    const float *cur_x = nullptr;    // the caller's NCHW input of the forward being enqueued
     float *p_params = nullptr, *p_grads = nullptr, *p_buffers = nullptr;
+    bf16 *p_params_bf16 = nullptr;   // bf16 mirror of the whole flat parameter vector (same offsets)
+    bf16 *own_bf16 = nullptr;        // model-owned default for the mirror
     void *slab = nullptr; size_t slab_bytes = 0;
     float *wgrad_ws = nullptr; size_t wgrad_floats = 0;
     bool weights_dirty = true;
     bool plans_ready = false;
     int conv_impl = 1;           // 0 = SIMT everywhere, 1 = tcgen05 where eligible
     int build_plans();
+    // CUDA-graph replay of forward / backward (launch-latency removal): one graph per distinct
+    // (input, output) pointer pair, captured on a private stream, replayed on the caller's
+    struct GraphEntry { const void *a; const void *b; cudaGraphExec_t exec; int64_t launches; };
+    bool use_graphs = true;
+    int eager_runs_fwd = 0, eager_runs_bwd = 0;
+    cudaStream_t cap_stream = nullptr;
+    std::vector<GraphEntry> fwd_graphs, bwd_graphs;
+    int forward_impl(const float *x_nchw, float *logits, cudaStream_t s);
+    int backward_impl(const float *dlogits, cudaStream_t s);
+    int run_graphed(std::vector<GraphEntry> &cache, const void *a, const void *b, bool is_fwd, cudaStream_t s);
+    void drop_graphs();
     int64_t steps_tracked = 0;
     bool profiling = false;
     std::vector<ProfRec> prof;

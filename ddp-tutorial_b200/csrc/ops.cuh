@@ -42,6 +42,25 @@ int op_maxpool_backward(const void *dy, const uint8_t *idx, void *dx, int dt, in
 int op_avgpool_forward(const void *x, int xdt, float *y, int N, int HW, int C, cudaStream_t s);
 int op_avgpool_backward(const float *dy, void *dx, int xdt, int N, int HW, int C, bool acc, cudaStream_t s);
 
+// 8-channel vectorised bf16 max pooling (C % 8 == 0, NHWC in and out)
+int op_maxpool_forward_bf16x8(const bf16 *x, bf16 *y, uint8_t *idx, int N, int Hi, int Wi, int C, int k, int stride,
+                              int pad, int Ho, int Wo, cudaStream_t s);
+int op_maxpool_backward_bf16x8(const bf16 *dy, const uint8_t *idx, bf16 *dx, int N, int Hi, int Wi, int C, int k,
+                               int stride, int pad, int Ho, int Wo, bool acc, cudaStream_t s);
+
+// ---- stem: fp32 NCHW image -> bf16 im2col rows [N*Ho*Wo][kpad] for a k x k / stride / pad conv,
+// column order (kh, kw, c) = the O,H,W,I weight order; columns >= k*k*C are zero
+int op_stem_im2col(const float *x_nchw, bf16 *col, int N, int C, int H, int W, int k, int stride, int pad, int Ho,
+                   int Wo, int kpad, cudaStream_t s);
+// dst[r][0:cols] = src[r][0:cols] for row pitches dpitch / spitch (fp32)
+int op_copy_2d_f32(const float *src, int spitch, float *dst, int dpitch, int rows, int cols, cudaStream_t s);
+
+// ---- small fully-connected head in fp32 (classifier: N <= 32 outputs) ------------------------
+int op_fc_forward(const float *x, const float *w, const float *bias, float *y, int B, int K, int N, bool relu, cudaStream_t s);
+// dw [N][K], db [N] (may be null), dx [B][K] (may be null; acc adds)
+int op_fc_backward(const float *x, const float *w, const float *dy, float *dw, float *db, float *dx, int B, int K, int N,
+                   bool acc_dx, cudaStream_t s);
+
 // ---- pointwise ------------------------------------------------------------------
 // dy = y > 0 ? dy : 0  (in place)
 int op_relu_mask(const void *y, void *dy, int dt, int64_t n, cudaStream_t s);
@@ -64,7 +83,8 @@ int conv_simt_wgrad(const ConvGeom &g, const void *x, const void *dy, int dt, fl
 // ---- loss / optimizer ------------------------------------------------------------------
 int op_ce_loss_grad(const float *logits, const int64_t *labels, int B, int C, float *loss,
                     float *dlogits, cudaStream_t s);
+// pb (optional): bf16 mirror of p, written in the same pass
 int op_sgd(float *p, const float *g, float *m, int64_t n, float lr, float momentum, float gscale,
-           int first, cudaStream_t s);
+           int first, bf16 *pb, cudaStream_t s);
 
 }  // namespace b2

@@ -124,13 +124,23 @@ k_bn_reduce(const T *__restrict__ x, const T *__restrict__ y, const T *__restric
     }
 }
 
-__global__ void k_bn_finalize_fwd(const float *__restrict__ partial, int nblk, int64_t M, int C, float eps,
-                                  float momentum, float *__restrict__ mean, float *__restrict__ invstd,
-                                  float *running_mean, float *running_var) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// one warp per channel: lanes stride over the row-block partials, fp64 combine
+__global__ void __launch_bounds__(128)
+k_bn_finalize_fwd(const float *__restrict__ partial, int nblk, int64_t M, int C, float eps,
+                  float momentum, float *__restrict__ mean, float *__restrict__ invstd,
+                  float *running_mean, float *running_var) {
+    const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
     double s0 = 0.0, s1 = 0.0;
-    for (int b = 0; b < nblk; ++b) { s0 += partial[((int64_t)b * 2) * C + c]; s1 += partial[((int64_t)b * 2 + 1) * C + c]; }
+    for (int b = lane; b < nblk; b += 32) { s0 += partial[((int64_t)b * 2) * C + c]; s1 += partial[((int64_t)b * 2 + 1) * C + c]; }
+    s0 = warp_sum_d(s0); s1 = warp_sum_d(s1);
+    if (lane != 0) return;
     double mu = s0 / (double)M;
     double var = s1 / (double)M - mu * mu;
     if (var < 0.0) var = 0.0;
@@ -172,7 +182,7 @@ int op_bn_forward(const void *x, void *y, const void *res, int dt, int64_t M, in
     dim3 grid((C + 31) / 32, w.row_blocks);
     DISPATCH_DT(dt, T, B2_LAUNCH((k_bn_reduce<T, false>), grid, 256, 0, s, (const T *)x, (const T *)nullptr,
                                  (const T *)nullptr, (const float *)nullptr, (const float *)nullptr, false, M, C, w.partial));
-    B2_LAUNCH(k_bn_finalize_fwd, (C + 127) / 128, 128, 0, s, w.partial, w.row_blocks, M, C, eps, momentum, w.mean,
+    B2_LAUNCH(k_bn_finalize_fwd, (C + 3) / 4, 128, 0, s, w.partial, w.row_blocks, M, C, eps, momentum, w.mean,
               w.invstd, running_mean, running_var);
     int64_t total = M * C;
     if (dt == DT_F32) {
@@ -185,13 +195,16 @@ int op_bn_forward(const void *x, void *y, const void *res, int dt, int64_t M, in
     return 0;
 }
 
-__global__ void k_bn_finalize_bwd(const float *__restrict__ partial, int nblk, int64_t M, int C,
-                                  const float *__restrict__ gamma, const float *__restrict__ invstd,
-                                  float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128)
+k_bn_finalize_bwd(const float *__restrict__ partial, int nblk, int64_t M, int C,
+                  const float *__restrict__ gamma, const float *__restrict__ invstd,
+                  float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef) {
+    const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
     double s0 = 0.0, s1 = 0.0;
-    for (int b = 0; b < nblk; ++b) { s0 += partial[((int64_t)b * 2) * C + c]; s1 += partial[((int64_t)b * 2 + 1) * C + c]; }
+    for (int b = lane; b < nblk; b += 32) { s0 += partial[((int64_t)b * 2) * C + c]; s1 += partial[((int64_t)b * 2 + 1) * C + c]; }
+    s0 = warp_sum_d(s0); s1 = warp_sum_d(s1);
+    if (lane != 0) return;
     dbeta[c] = (float)s0;
     dgamma[c] = (float)s1;
     coef[c] = gamma[c] * invstd[c];
@@ -238,7 +251,7 @@ int op_bn_backward(const void *x, const void *y, const void *dy, void *dx, void 
     dim3 grid((C + 31) / 32, w.row_blocks);
     DISPATCH_DT(dt, T, B2_LAUNCH((k_bn_reduce<T, true>), grid, 256, 0, s, (const T *)x, (const T *)y, (const T *)dy,
                                  w.mean, w.invstd, relu, M, C, w.partial));
-    B2_LAUNCH(k_bn_finalize_bwd, (C + 127) / 128, 128, 0, s, w.partial, w.row_blocks, M, C, gamma, w.invstd, dgamma,
+    B2_LAUNCH(k_bn_finalize_bwd, (C + 3) / 4, 128, 0, s, w.partial, w.row_blocks, M, C, gamma, w.invstd, dgamma,
               dbeta, w.coef);
     int64_t total = M * C;
     if (dt == DT_F32) {
@@ -429,7 +442,7 @@ int op_ce_loss_grad(const float *logits, const int64_t *labels, int B, int C, fl
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_sgd(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, int64_t n, float lr, float mom,
-      float gscale, int first) {
+      float gscale, int first, bf16 *__restrict__ pb) {
     int64_t n4 = n >> 2;
     float4 *p4 = (float4 *)p; const float4 *g4 = (const float4 *)g; float4 *m4 = (float4 *)m;
     // torch semantics (sgd.py:_single_tensor_sgd): buf.mul_(momentum).add_(grad) is two
@@ -445,18 +458,228 @@ k_sgd(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
         }
         pv.x = fmaf(-lr, mv.x, pv.x); pv.y = fmaf(-lr, mv.y, pv.y); pv.z = fmaf(-lr, mv.z, pv.z); pv.w = fmaf(-lr, mv.w, pv.w);
         m4[i] = mv; p4[i] = pv;
+        if (pb) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y), hi = __floats2bfloat162_rn(pv.z, pv.w);
+            uint2 pk; pk.x = *(uint32_t *)&lo; pk.y = *(uint32_t *)&hi;
+            ((uint2 *)pb)[i] = pk;
+        }
     }
     for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float gv = gscale != 1.f ? __fmul_rn(g[i], gscale) : g[i];
         float mv = first ? gv : __fadd_rn(__fmul_rn(m[i], mom), gv);
-        m[i] = mv; p[i] = fmaf(-lr, mv, p[i]);
+        m[i] = mv; float pn = fmaf(-lr, mv, p[i]); p[i] = pn;
+        if (pb) pb[i] = __float2bfloat16_rn(pn);
     }
 }
-int op_sgd(float *p, const float *g, float *m, int64_t n, float lr, float momentum, float gscale, int first, cudaStream_t s) {
+int op_sgd(float *p, const float *g, float *m, int64_t n, float lr, float momentum, float gscale, int first, bf16 *pb,
+           cudaStream_t s) {
     if (n <= 0) return 0;
     B2_CHECK(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0), B2_ERR_ARG,
              "sgd: p/g/m must be 16-byte aligned");
-    B2_LAUNCH(k_sgd, grid_for(ceil_div(n, 4), 256, kNumSMs * 8), 256, 0, s, p, g, m, n, lr, momentum, gscale, first);
+    B2_CHECK(((uintptr_t)pb % 8) == 0, B2_ERR_ARG, "sgd: bf16 mirror must be 8-byte aligned");
+    B2_LAUNCH(k_sgd, grid_for(ceil_div(n, 4), 256, kNumSMs * 8), 256, 0, s, p, g, m, n, lr, momentum, gscale, first, pb);
+    return 0;
+}
+
+}  // namespace b2
+
+// =====================================================================================
+// round-1 additions: vectorised bf16 max pooling, stem im2col, fp32 classifier head
+// =====================================================================================
+namespace b2 {
+
+static inline int grid_for2(int64_t n, int block, int max_blocks = kNumSMs * 16) {
+    int64_t b = ceil_div(n, block);
+    if (b > max_blocks) b = max_blocks;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+__global__ void __launch_bounds__(256)
+k_maxpool_fwd_bf16x8(const bf16 *__restrict__ x, bf16 *__restrict__ y, uint8_t *__restrict__ idx, int N, int Hi, int Wi,
+                     int C, int k, int stride, int pad, int Ho, int Wo) {
+    const int C8 = C >> 3;
+    const int64_t total = (int64_t)N * Ho * Wo * C8;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c8 = i % C8; int64_t r = i / C8;
+        int ow = r % Wo; r /= Wo;
+        int oh = r % Ho; int n = r / Ho;
+        float best[8]; int bi[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bi[e] = 255; }
+        for (int a = 0; a < k; ++a) {
+            int hi = oh * stride - pad + a;
+            if (hi < 0 || hi >= Hi) continue;
+            for (int b = 0; b < k; ++b) {
+                int wi = ow * stride - pad + b;
+                if (wi < 0 || wi >= Wi) continue;
+                uint4 raw = *(const uint4 *)(x + (((int64_t)n * Hi + hi) * Wi + wi) * C + c8 * 8);
+                const bf16 *v = (const bf16 *)&raw;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float f = __bfloat162float(v[e]);
+                    if (f > best[e] || bi[e] == 255) { best[e] = f; bi[e] = a * k + b; }
+                }
+            }
+        }
+        __align__(16) bf16 o[8]; __align__(8) uint8_t ix[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { o[e] = __float2bfloat16_rn(best[e]); ix[e] = (uint8_t)bi[e]; }
+        *(uint4 *)(y + i * 8) = *(uint4 *)o;
+        *(uint2 *)(idx + i * 8) = *(uint2 *)ix;
+    }
+}
+int op_maxpool_forward_bf16x8(const bf16 *x, bf16 *y, uint8_t *idx, int N, int Hi, int Wi, int C, int k, int stride,
+                              int pad, int Ho, int Wo, cudaStream_t s) {
+    B2_CHECK(C % 8 == 0, B2_ERR_ARG, "maxpool x8: C must be a multiple of 8");
+    int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+    B2_LAUNCH(k_maxpool_fwd_bf16x8, grid_for2(total, 256), 256, 0, s, x, y, idx, N, Hi, Wi, C, k, stride, pad, Ho, Wo);
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_maxpool_bwd_bf16x8(const bf16 *__restrict__ dy, const uint8_t *__restrict__ idx, bf16 *__restrict__ dx, int N, int Hi,
+                     int Wi, int C, int k, int stride, int pad, int Ho, int Wo, bool acc) {
+    const int C8 = C >> 3;
+    const int64_t total = (int64_t)N * Hi * Wi * C8;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c8 = i % C8; int64_t r = i / C8;
+        int wi = r % Wi; r /= Wi;
+        int hi = r % Hi; int n = r / Hi;
+        float g[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = 0.f;
+        int oh_lo = hi + pad - k + stride; oh_lo = oh_lo < 0 ? 0 : oh_lo / stride;
+        int oh_hi = (hi + pad) / stride; if (oh_hi > Ho - 1) oh_hi = Ho - 1;
+        int ow_lo = wi + pad - k + stride; ow_lo = ow_lo < 0 ? 0 : ow_lo / stride;
+        int ow_hi = (wi + pad) / stride; if (ow_hi > Wo - 1) ow_hi = Wo - 1;
+        for (int oh = oh_lo; oh <= oh_hi; ++oh)
+            for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+                const int mine = (hi - (oh * stride - pad)) * k + (wi - (ow * stride - pad));
+                const int64_t o = ((((int64_t)n * Ho + oh) * Wo + ow) * C8 + c8) * 8;
+                uint2 iraw = *(const uint2 *)(idx + o);
+                uint4 draw = *(const uint4 *)(dy + o);
+                const uint8_t *ix = (const uint8_t *)&iraw; const bf16 *dv = (const bf16 *)&draw;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (ix[e] == mine) g[e] += __bfloat162float(dv[e]);
+            }
+        __align__(16) bf16 o8[8];
+        if (acc) {
+            uint4 old = *(const uint4 *)(dx + i * 8);
+            const bf16 *ov = (const bf16 *)&old;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] += __bfloat162float(ov[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o8[e] = __float2bfloat16_rn(g[e]);
+        *(uint4 *)(dx + i * 8) = *(uint4 *)o8;
+    }
+}
+int op_maxpool_backward_bf16x8(const bf16 *dy, const uint8_t *idx, bf16 *dx, int N, int Hi, int Wi, int C, int k,
+                               int stride, int pad, int Ho, int Wo, bool acc, cudaStream_t s) {
+    B2_CHECK(C % 8 == 0, B2_ERR_ARG, "maxpool x8: C must be a multiple of 8");
+    int64_t total = (int64_t)N * Hi * Wi * (C / 8);
+    B2_LAUNCH(k_maxpool_bwd_bf16x8, grid_for2(total, 256), 256, 0, s, dy, idx, dx, N, Hi, Wi, C, k, stride, pad, Ho, Wo, acc);
+    return 0;
+}
+
+// ---- stem im2col: one thread per (output pixel, 8 consecutive columns) -> one 16-byte store
+__global__ void __launch_bounds__(256)
+k_stem_im2col(const float *__restrict__ x, bf16 *__restrict__ col, int N, int C, int H, int W, int k, int stride, int pad,
+              int Ho, int Wo, int kpad) {
+    const int chunks = kpad >> 3;
+    const int K = k * k * C;
+    const int64_t total = (int64_t)N * Ho * Wo * chunks;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int ch = i % chunks; int64_t m = i / chunks;
+        int wo = m % Wo; int64_t t = m / Wo;
+        int ho = t % Ho; int n = (int)(t / Ho);
+        __align__(16) bf16 o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int kk = ch * 8 + e;
+            float v = 0.f;
+            if (kk < K) {
+                int c = kk % C; int tap = kk / C;
+                int kw = tap % k, kh = tap / k;
+                int hi = ho * stride - pad + kh, wi = wo * stride - pad + kw;
+                if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = __ldg(x + (((int64_t)n * C + c) * H + hi) * W + wi);
+            }
+            o[e] = __float2bfloat16_rn(v);
+        }
+        *(uint4 *)(col + m * kpad + ch * 8) = *(uint4 *)o;
+    }
+}
+int op_stem_im2col(const float *x_nchw, bf16 *col, int N, int C, int H, int W, int k, int stride, int pad, int Ho, int Wo,
+                   int kpad, cudaStream_t s) {
+    B2_CHECK(kpad % 8 == 0 && kpad >= k * k * C, B2_ERR_ARG, "stem im2col: bad kpad %d", kpad);
+    int64_t total = (int64_t)N * Ho * Wo * (kpad / 8);
+    B2_LAUNCH(k_stem_im2col, grid_for2(total, 256), 256, 0, s, x_nchw, col, N, C, H, W, k, stride, pad, Ho, Wo, kpad);
+    return 0;
+}
+
+__global__ void k_copy_2d_f32(const float *__restrict__ src, int spitch, float *__restrict__ dst, int dpitch, int rows, int cols) {
+    int64_t total = (int64_t)rows * cols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = i % cols; int r = (int)(i / cols);
+        dst[(int64_t)r * dpitch + c] = src[(int64_t)r * spitch + c];
+    }
+}
+int op_copy_2d_f32(const float *src, int spitch, float *dst, int dpitch, int rows, int cols, cudaStream_t s) {
+    B2_LAUNCH(k_copy_2d_f32, grid_for2((int64_t)rows * cols, 256), 256, 0, s, src, spitch, dst, dpitch, rows, cols);
+    return 0;
+}
+
+// ---- classifier head, fp32.  forward: one warp per sample; N <= 32 outputs
+__global__ void __launch_bounds__(256)
+k_fc_fwd(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias, float *__restrict__ y,
+         int B, int K, int N, bool relu) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const float *xr = x + (int64_t)warp * K;
+    for (int n = 0; n < N; ++n) {
+        const float *wr = w + (int64_t)n * K;
+        float s = 0.f;
+        for (int kk = lane; kk < K; kk += 32) s = fmaf(xr[kk], wr[kk], s);
+        s = warp_sum(s);
+        if (lane == 0) {
+            if (bias) s += bias[n];
+            if (relu) s = s > 0.f ? s : 0.f;
+            y[(int64_t)warp * N + n] = s;
+        }
+    }
+}
+int op_fc_forward(const float *x, const float *w, const float *bias, float *y, int B, int K, int N, bool relu, cudaStream_t s) {
+    B2_LAUNCH(k_fc_fwd, (int)ceil_div((int64_t)B * 32, 256), 256, 0, s, x, w, bias, y, B, K, N, relu);
+    return 0;
+}
+// dW[n][k] = sum_b dy[b][n] x[b][k]: grid (K/128, N), fixed summation order over b (deterministic)
+__global__ void __launch_bounds__(128)
+k_fc_wgrad(const float *__restrict__ x, const float *__restrict__ dy, float *__restrict__ dw, float *__restrict__ db,
+           int B, int K, int N) {
+    const int kk = blockIdx.x * 128 + threadIdx.x, n = blockIdx.y;
+    float s = 0.f, sb = 0.f;
+    if (kk < K)
+        for (int b = 0; b < B; ++b) { float d = dy[(int64_t)b * N + n]; s = fmaf(d, x[(int64_t)b * K + kk], s); sb += d; }
+    if (kk < K) dw[(int64_t)n * K + kk] = s;
+    if (db && kk == 0) db[n] = sb;
+}
+__global__ void __launch_bounds__(256)
+k_fc_dgrad(const float *__restrict__ w, const float *__restrict__ dy, float *__restrict__ dx, int B, int K, int N, bool acc) {
+    const int64_t total = (int64_t)B * K;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int kk = i % K; int64_t b = i / K;
+        float s = 0.f;
+        for (int n = 0; n < N; ++n) s = fmaf(dy[b * N + n], w[(int64_t)n * K + kk], s);
+        if (acc) s += dx[i];
+        dx[i] = s;
+    }
+}
+int op_fc_backward(const float *x, const float *w, const float *dy, float *dw, float *db, float *dx, int B, int K, int N,
+                   bool acc_dx, cudaStream_t s) {
+    dim3 grid((unsigned)ceil_div(K, 128), (unsigned)N);
+    B2_LAUNCH(k_fc_wgrad, grid, 128, 0, s, x, dy, dw, db, B, K, N);
+    if (dx) B2_LAUNCH(k_fc_dgrad, grid_for2((int64_t)B * K, 256), 256, 0, s, w, dy, dx, B, K, N, acc_dx);
     return 0;
 }
 

@@ -95,12 +95,15 @@ class Engine:
         self.flat_params: Optional[torch.Tensor] = None
         self.flat_grads: Optional[torch.Tensor] = None
         self.flat_buffers: Optional[torch.Tensor] = None
+        self.flat_params_bf16: Optional[torch.Tensor] = None   # bf16 mirror shared by all batch sizes
         self.param_views: List[torch.Tensor] = []
         self._host_init: Optional[Dict[str, torch.Tensor]] = None
         self._last_batch: Optional[int] = None
         self.ddp = None            # set by DistributedDataParallel
         self.optimizer = None      # set by SGD when built from our parameters
         self._keep = []            # objects that must outlive the vectors (comm allocations)
+        self._logits: Dict[int, torch.Tensor] = {}
+        self._dlogits: Dict[int, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ layout
     def _probe_layout(self, device_index: int):
@@ -113,6 +116,8 @@ class Engine:
             if device_index is None:
                 device_index = self.device.index
             m = _CModel(self.kind, batch, self.num_classes, self.precision, device_index)
+            if not getattr(self, "_graphs", True):
+                call("b2_model_set_graphs", m.h, 0)
             if self.flat_params is not None:
                 self._bind(m)
             self.models[batch] = m
@@ -121,6 +126,8 @@ class Engine:
     def _bind(self, m: _CModel):
         call("b2_model_bind", m.h, C.c_void_p(self.flat_params.data_ptr()), C.c_void_p(self.flat_grads.data_ptr()),
              C.c_void_p(self.flat_buffers.data_ptr()) if self.n_buffers else None)
+        if self.flat_params_bf16 is not None:
+            call("b2_model_bind_bf16", m.h, C.c_void_p(self.flat_params_bf16.data_ptr()))
 
     # ------------------------------------------------------------------ placement
     def to(self, device, host_params: Dict[str, torch.Tensor], host_buffers: Dict[str, torch.Tensor]):
@@ -140,6 +147,8 @@ class Engine:
         self.flat_params = alloc(max(self.n_params, 4))
         self.flat_grads = alloc(max(self.n_params, 4))
         self.flat_buffers = alloc(max(self.n_buffers, 4))
+        if self.precision == "bf16" and self.flat_params_bf16 is None:
+            self.flat_params_bf16 = torch.zeros(max(self.n_params, 64), dtype=torch.bfloat16, device=self.flat_params.device)
         if old[0] is not None:
             self.flat_params.copy_(old[0]); self.flat_grads.copy_(old[1]); self.flat_buffers.copy_(old[2])
         self.param_views = []
@@ -169,6 +178,10 @@ class Engine:
         for m in self.models.values():
             call("b2_model_mark_weights_dirty", m.h)
 
+    def mark_weights_clean(self):
+        for m in self.models.values():
+            call("b2_model_mark_weights_clean", m.h)
+
     # ------------------------------------------------------------------ step pieces
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.device is None:
@@ -181,7 +194,13 @@ class Engine:
             raise B2Error("empty batch")
         x = x.contiguous()
         m = self._model(x.shape[0])
-        logits = torch.empty(x.shape[0], self.num_classes, dtype=torch.float32, device=self.device)
+        # persistent output buffer per batch size: stable addresses let the library replay its
+        # captured CUDA graph instead of re-launching ~200 kernels (the returned tensor is
+        # overwritten by the next forward of the same batch size)
+        logits = self._logits.get(x.shape[0])
+        if logits is None:
+            logits = torch.empty(x.shape[0], self.num_classes, dtype=torch.float32, device=self.device)
+            self._logits[x.shape[0]] = logits
         call("b2_forward", m.h, C.c_void_p(x.data_ptr()), C.c_void_p(logits.data_ptr()), _stream_ptr())
         self._last_batch = x.shape[0]
         logits._b2_engine = self
@@ -195,6 +214,18 @@ class Engine:
         call("b2_backward", m.h, C.c_void_p(dlogits.data_ptr()), _stream_ptr())
         if self.ddp is not None:
             self.ddp._after_backward()
+
+    def dlogits_buffer(self, batch: int) -> torch.Tensor:
+        d = self._dlogits.get(batch)
+        if d is None:
+            d = torch.empty(batch, self.num_classes, dtype=torch.float32, device=self.device)
+            self._dlogits[batch] = d
+        return d
+
+    def set_graphs(self, enable: bool):
+        for m in self.models.values():
+            call("b2_model_set_graphs", m.h, int(enable))
+        self._graphs = enable
 
     def steps_tracked(self) -> int:
         return sum(lib().b2_model_steps_tracked(m.h) for m in self.models.values())

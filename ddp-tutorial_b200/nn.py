@@ -262,7 +262,7 @@ class CrossEntropyLoss:
             raise B2Error(f"labels on {labels.device}, outputs on {outputs.device}")
         labels = labels.contiguous()
         loss = torch.empty(1, dtype=torch.float32, device=outputs.device)
-        dlogits = torch.empty_like(outputs)
+        dlogits = engine.dlogits_buffer(outputs.shape[0])
         call("b2_ce_loss_grad", C.c_void_p(outputs.data_ptr()), C.c_void_p(labels.data_ptr()), outputs.shape[0],
              outputs.shape[1], C.c_void_p(loss.data_ptr()), C.c_void_p(dlogits.data_ptr()), _stream_ptr())
         return Loss(engine, loss, dlogits, (outputs, labels))

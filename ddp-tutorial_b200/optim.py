@@ -44,8 +44,12 @@ class SGD:
         if e.ddp is not None:
             e.ddp._optimizer_step(self, first)
         else:
+            mirror = e.flat_params_bf16
             call("b2_sgd", C.c_void_p(e.flat_params.data_ptr()), C.c_void_p(e.flat_grads.data_ptr()),
                  C.c_void_p(self.momentum_buffer.data_ptr()), e.n_params, self.lr, self.momentum, 1.0, first,
-                 _stream_ptr())
+                 C.c_void_p(mirror.data_ptr()) if mirror is not None else None, _stream_ptr())
+            if mirror is not None:
+                e.mark_weights_clean()          # the bf16 mirror was written by the same kernel
+            else:
+                e.mark_weights_dirty()
         self.state_steps += 1
-        e.mark_weights_dirty()

@@ -183,6 +183,7 @@ class DistributedDataParallel:
         e = self.engine
         call("b2_allreduce_sgd", C.c_void_p(opt.momentum_buffer.data_ptr()), e.n_params, opt.lr, opt.momentum,
              first, self.algo, _stream_ptr())
+        e.mark_weights_dirty()
 
     def allreduce_grads(self):
         """Unfused form (gradients averaged in place on every rank) -- for tests and for users

@@ -76,6 +76,12 @@ int b2_model_bind(b2_model *m, float *params, float *grads, float *buffers);
 /* bf16 mode: refresh the bf16 compute copies of the weights from the fp32
  * masters (done automatically by b2_sgd_step_model; call after loading params) */
 int b2_model_sync_weights(b2_model *m, void *stream);
+/* bf16 mode: use a caller-owned bf16 mirror of the flat parameter vector (same element
+ * offsets, 128-byte aligned) instead of the model's own; lets one optimizer kernel keep the
+ * mirror of several models (batch sizes) current.  NULL restores the model-owned mirror. */
+int b2_model_bind_bf16(b2_model *m, void *bf16_params);
+/* the caller refreshed the mirror itself (b2_sgd with p_bf16) */
+int b2_model_mark_weights_clean(b2_model *m);
 /* tell the model that the bound fp32 parameters changed behind its back (optimizer
  * step, load_state_dict): bf16 compute copies are refreshed before the next forward */
 int b2_model_mark_weights_dirty(b2_model *m);
@@ -85,6 +91,9 @@ int b2_forward(b2_model *m, const float *x_nchw, float *logits, void *stream);
 /* loss.backward(): cifar_example_ddp.py:106.  dlogits fp32 [batch,num_classes];
  * writes every parameter gradient into the bound flat grad vector */
 int b2_backward(b2_model *m, const float *dlogits, void *stream);
+/* forward/backward are replayed from CUDA graphs after two eager calls (default on); one graph
+ * per distinct (input, output) pointer pair.  0 disables and drops the cached graphs. */
+int b2_model_set_graphs(b2_model *m, int enable);
 /* measurement: when enabled, forward/backward bracket every op with CUDA events on the
  * launching stream; collect() synchronises and returns, per category (B2_PROF_*), the summed
  * milliseconds, algorithmic FLOPs, algorithmic bytes and number of op launches since the last
@@ -121,7 +130,7 @@ int b2_ce_loss_grad(const float *logits, const int64_t *labels, int batch, int c
  * grad on the first step), else m = momentum*m + g; p -= lr*m.  grad_scale
  * multiplies g first (1/world or loss-scale inverse; pass 1.0f for none). */
 int b2_sgd(float *p, const float *g, float *m, int64_t n, float lr, float momentum,
-           float grad_scale, int first_step, void *stream);
+           float grad_scale, int first_step, void *p_bf16 /* optional bf16 mirror of p */, void *stream);
 
 /* ---- peer-memory communicator: replaces init_process_group('nccl') + DDP's
  * Reducer all-reduce (cifar_example_ddp.py:42-58,83; reducer.hpp:524) ---------- */

@@ -69,7 +69,7 @@ def test_sgd_matches_oracle_to_one_ulp_on_ragged_sizes():
         for i, g in enumerate((g1, g2)):
             q, m = O.sgd_momentum_update(q, g, m)
             gd = g.to(DEV)
-            b2._lib.call("b2_sgd", _vp(pd), _vp(gd), _vp(md), n, 0.001, 0.9, 1.0, 1 if i == 0 else 0, None)
+            b2._lib.call("b2_sgd", _vp(pd), _vp(gd), _vp(md), n, 0.001, 0.9, 1.0, 1 if i == 0 else 0, None, None)
         torch.cuda.synchronize()
         np.testing.assert_allclose(pd.cpu().numpy(), q.numpy(), rtol=2.4e-7, atol=1e-9)
         np.testing.assert_allclose(md.cpu().numpy(), m.numpy(), rtol=2.4e-7, atol=1e-9)
@@ -184,14 +184,26 @@ def test_resnet18_state_dict_keys_match_torchvision():
 
 
 def test_resnet50_fp32_step0():
+    """ResNet-50 at 1x1 spatial in layer4 is so ill-conditioned that torch's own fp32 CPU
+    gradients are 30% (max-norm) off its fp64 gradients at B=32
+    (profiles/r01_parity_diag_resnet50_fp32.txt).  Gate: loss within 2e-4 of the fp32 oracle and
+    our gradient no further from the fp64 oracle than the fp32 oracle itself is."""
     r = O.train("resnet50", seed=0, batch=32, steps=1)
     r64 = O.train("resnet50", seed=0, batch=32, steps=1, dtype=torch.float64)
     torch.manual_seed(0)
     net = b2.resnet50(num_classes=10, precision="fp32").to(DEV)
     losses, grads0 = run_b2(net, r["x"], r["y"], 1)
     assert abs(losses[0] - r["loss"][0]) < 2e-4, (losses[0], r["loss"][0])
-    worst = _grad_report(grads0, r64["grads0"])
-    assert worst[0][0] < 1e-3, worst[:8]
+    truth = torch.cat([g.flatten() for _, g in r64["grads0"]])
+    mine = torch.cat([grads0[n].flatten() for n, _ in r64["grads0"]]).double()
+    cpu32 = torch.cat([g.flatten() for _, g in r["grads0"]]).double()
+    rel = lambda a: float((a - truth).norm() / truth.norm())
+    assert rel(mine) < 1.5 * rel(cpu32) + 1e-3, (rel(mine), rel(cpu32))
+    # the early layers are well conditioned: per-tensor check there
+    worst = [w for w in _grad_report(grads0, r64["grads0"]) if w[1].startswith(("conv1", "bn1", "layer1"))]
+    ref = {n: e for e, n in _grad_report({n: g for n, g in r["grads0"]}, r64["grads0"])}
+    for e, n in worst:
+        assert e < 3 * ref[n] + 1e-4, (n, e, ref[n])
 
 
 def _autocast_grads(name, x, y):

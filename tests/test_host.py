@@ -52,8 +52,8 @@ def test_fails_loudly_without_gpu():
 
 def test_bad_arguments_are_rejected():
     l = b2.lib()
-    assert l.b2_sgd(None, None, None, -1, 0.1, 0.9, 1.0, 0, None) != 0
-    assert l.b2_sgd(None, None, None, 0, 0.1, 0.9, 1.0, 0, None) == 0          # empty is a no-op
+    assert l.b2_sgd(None, None, None, -1, 0.1, 0.9, 1.0, 0, None, None) != 0
+    assert l.b2_sgd(None, None, None, 0, 0.1, 0.9, 1.0, 0, None, None) == 0          # empty is a no-op
     assert l.b2_ce_loss_grad(None, None, 4, 10, None, None, None) != 0
     assert l.b2_model_create(0, 0, 10, 0, 0, ctypes.byref(ctypes.c_void_p())) != 0
     assert l.b2_comm_register(None, None, None, 0) != 0
