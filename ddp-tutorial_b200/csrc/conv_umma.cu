@@ -181,6 +181,7 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         uint32_t v[32];
+        float *sT = (float *)sA;                       // [128][65] fp32 staging for the BN statistics
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + half * 32, v);
@@ -202,7 +203,25 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
 #pragma unroll
                 for (int e = 0; e < 4; ++e) p2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
                 d4[j] = pk;
+                if (p.stats) {                         // statistics of the values BatchNorm will read (bf16-rounded)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float2 rf = __bfloat1622float2(p2[e]);
+                        sT[r * 65 + half * 32 + j * 8 + 2 * e] = rf.x;
+                        sT[r * 65 + half * 32 + j * 8 + 2 * e + 1] = rf.y;
+                    }
+                }
             }
+        }
+        if (p.stats) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+            const int e = (warp - 2) * 32 + lane;
+            const int c = e & 63, r0 = (e >> 6) * 64;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+            for (int rr = 0; rr < 64; ++rr) { float x = sT[(r0 + rr) * 65 + c]; s0 += x; s1 = fmaf(x, x, s1); }
+            atomicAdd(p.stats + ch0 + c, s0);
+            atomicAdd(p.stats + p.out_C + ch0 + c, s1);
         }
         tc_fence_before();
     }

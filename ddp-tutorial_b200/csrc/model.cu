@@ -254,6 +254,17 @@ int Model::finalize() {
             }
         }
     }
+    // fused BatchNorm: producer conv runs on the tcgen05 path (its epilogue emits the statistics)
+    size_t sums_floats = 0;
+    std::vector<size_t> sum_off(ops.size(), 0);
+    for (size_t i = 0; i < ops.size(); ++i) {
+        Op &o = ops[i];
+        if (o.type != OP_BN) continue;
+        for (const Op &c : ops)
+            if (c.type == OP_CONV && c.out == o.in && (c.use_umma || c.stem_umma)) o.bn_fused = true;
+        if (o.bn_fused) { sum_off[i] = sums_floats; sums_floats += 4 * (size_t)tensors[o.in].C; }
+    }
+    size_t sums_off = reserve(sums_floats * 4 + 256);
     size_t wg_off = reserve(wg_floats * 4 + 256);
     size_t bf_off = precision == B2_PREC_BF16 ? reserve((size_t)n_params * 2 + 256) : 0;
     wgrad_floats = wg_floats;
@@ -274,6 +285,11 @@ int Model::finalize() {
         }
     }
     wgrad_ws = (float *)(base + wg_off);
+    bn_sums = (float *)(base + sums_off); bn_sums_bytes = sums_floats * 4;
+    for (size_t i = 0; i < ops.size(); ++i)
+        if (ops[i].type == OP_BN && ops[i].bn_fused) {
+            ops[i].fsum = bn_sums + sum_off[i]; ops[i].bsum = ops[i].fsum + 2 * (size_t)tensors[ops[i].in].C;
+        }
     if (precision == B2_PREC_BF16) { own_bf16 = (bf16 *)(base + bf_off); p_params_bf16 = own_bf16; }
     return 0;
 }
@@ -350,6 +366,11 @@ int Model::build_plans() {
         B2_TRY(umma_wgrad_zero_dead(o.wplan, 0));      // once: dead-tap gradients are exactly zero and never rewritten
     }
     B2_CUDA(cudaStreamSynchronize(0));
+    for (Op &b : ops) {
+        if (b.type != OP_BN || !b.bn_fused) continue;
+        for (Op &c : ops)
+            if (c.type == OP_CONV && c.out == b.in) c.fplan.p.stats = b.fsum;
+    }
     plans_ready = true;
     return 0;
 }
@@ -407,6 +428,7 @@ int Model::forward(const float *x_nchw, float *logits, cudaStream_t s) {
 
 int Model::forward_impl(const float *x_nchw, float *logits, cudaStream_t s) {
     cur_x = x_nchw;
+    if (bn_sums_bytes) B2_CUDA(cudaMemsetAsync(bn_sums, 0, bn_sums_bytes, s));
 
     for (Op &o : ops) {
         Tensor &to = tensors[o.out];
@@ -454,6 +476,11 @@ int Model::forward_impl(const float *x_nchw, float *logits, cudaStream_t s) {
             Tensor &ti = tensors[o.in];
             int64_t M = (int64_t)ti.N * ti.H * ti.W;
             int ph = prof_begin(PC_BN_FWD, 0, ti.numel * (double)dt_size(ti.dt) * (o.res >= 0 ? 4.0 : 3.0), s);
+            if (o.bn_fused)
+                B2_TRY(op_bn_forward_fused(ti.val, to.val, o.res >= 0 ? tensors[o.res].val : nullptr, ti.dt, M, ti.C, o.fsum,
+                                           p_params + o.w_off, p_params + o.b_off, p_buffers ? p_buffers + o.rm_off : nullptr,
+                                           p_buffers ? p_buffers + o.rv_off : nullptr, 1e-5f, 0.1f, o.relu, o.bn, s));
+            else
             B2_TRY(op_bn_forward(ti.val, to.val, o.res >= 0 ? tensors[o.res].val : nullptr, ti.dt, M, ti.C,
                                  p_params + o.w_off, p_params + o.b_off, p_buffers ? p_buffers + o.rm_off : nullptr,
                                  p_buffers ? p_buffers + o.rv_off : nullptr, 1e-5f, 0.1f, o.relu, o.bn, s));
@@ -540,6 +567,11 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
         case OP_BN: {
             int64_t M = (int64_t)ti.N * ti.H * ti.W;
             int ph = prof_begin(PC_BN_BWD, 0, ti.numel * (double)dt_size(ti.dt) * (o.res >= 0 ? 7.0 : 6.0), s);
+            if (o.bn_fused)
+                B2_TRY(op_bn_backward_fused(ti.val, to.val, to.grad, ti.grad, o.res >= 0 ? tensors[o.res].grad : nullptr, ti.dt, M,
+                                            ti.C, o.bsum, p_params + o.w_off, p_grads + o.w_off, p_grads + o.b_off, o.relu,
+                                            o.acc_in, o.acc_res, o.bn, s));
+            else
             B2_TRY(op_bn_backward(ti.val, to.val, to.grad, ti.grad, o.res >= 0 ? tensors[o.res].grad : nullptr, ti.dt, M,
                                   ti.C, p_params + o.w_off, p_grads + o.w_off, p_grads + o.b_off, o.relu, o.acc_in,
                                   o.acc_res, o.bn, s));

@@ -25,6 +25,8 @@ struct Op {
     bool relu, out_nchw;
     bool need_dgrad, acc_in, acc_res;
     BnWork bn;
+    bool bn_fused;               // statistics come from the producing conv's epilogue
+    float *fsum, *bsum;          // [2][C] each, inside the per-step zeroed arena
     uint8_t *idx;                // maxpool argmax
     int wdt, wpitch;             // conv: weight operand type / row pitch as the kernels see it
     bool use_umma;               // tcgen05 path (bf16, channel counts multiples of 64)
@@ -60,6 +62,7 @@ struct Model {
     bf16 *own_bf16 = nullptr;        // model-owned default for the mirror
     void *slab = nullptr; size_t slab_bytes = 0;
     float *wgrad_ws = nullptr; size_t wgrad_floats = 0;
+    float *bn_sums = nullptr; size_t bn_sums_bytes = 0;    // all fused-BN sum buffers, zeroed once per step
     bool weights_dirty = true;
     bool plans_ready = false;
     int conv_impl = 1;           // 0 = SIMT everywhere, 1 = tcgen05 where eligible

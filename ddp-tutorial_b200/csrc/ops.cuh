@@ -32,6 +32,17 @@ int op_bn_backward(const void *x, const void *y, const void *dy, void *dx, void 
                    int64_t M, int C, const float *gamma, float *dgamma, float *dbeta, bool relu,
                    bool acc_dx, bool acc_dres, const BnWork &w, cudaStream_t s);
 
+// Fused variants (bf16 tcgen05 path): the producing conv's epilogue already accumulated the
+// per-channel sum / sum of squares into fsum[2][C] (atomics, zeroed once per step), so forward is
+// ONE kernel (finalize per block in shared memory + apply); backward is a reduce (atomics into
+// bsum[2][C]) plus an apply that derives its coefficients per block.
+int op_bn_forward_fused(const void *x, void *y, const void *res, int dt, int64_t M, int C, const float *fsum,
+                        const float *gamma, const float *beta, float *running_mean, float *running_var, float eps,
+                        float momentum, bool relu, const BnWork &w, cudaStream_t s);
+int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx, void *dres, int dt, int64_t M, int C,
+                         float *bsum, const float *gamma, float *dgamma, float *dbeta, bool relu, bool acc_dx,
+                         bool acc_dres, const BnWork &w, cudaStream_t s);
+
 // ---- pooling -------------------------------------------------------------------
 int op_maxpool_forward(const void *x, void *y, uint8_t *idx, int dt, int N, int Hi, int Wi, int C,
                        int k, int stride, int pad, int Ho, int Wo, bool out_nchw, cudaStream_t s);

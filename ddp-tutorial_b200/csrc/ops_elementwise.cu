@@ -637,11 +637,18 @@ k_fc_fwd(const float *__restrict__ x, const float *__restrict__ w, const float *
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
     const float *xr = x + (int64_t)warp * K;
-    for (int n = 0; n < N; ++n) {
-        const float *wr = w + (int64_t)n * K;
-        float s = 0.f;
-        for (int kk = lane; kk < K; kk += 32) s = fmaf(xr[kk], wr[kk], s);
-        s = warp_sum(s);
+    float acc[32];
+#pragma unroll
+    for (int n = 0; n < 32; ++n) acc[n] = 0.f;
+    for (int kk = lane; kk < K; kk += 32) {
+        const float xv = xr[kk];
+#pragma unroll
+        for (int n = 0; n < 32; ++n) if (n < N) acc[n] = fmaf(xv, __ldg(w + (int64_t)n * K + kk), acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+        if (n >= N) break;
+        float s = warp_sum(acc[n]);
         if (lane == 0) {
             if (bias) s += bias[n];
             if (relu) s = s > 0.f ? s : 0.f;
@@ -653,16 +660,34 @@ int op_fc_forward(const float *x, const float *w, const float *bias, float *y, i
     B2_LAUNCH(k_fc_fwd, (int)ceil_div((int64_t)B * 32, 256), 256, 0, s, x, w, bias, y, B, K, N, relu);
     return 0;
 }
-// dW[n][k] = sum_b dy[b][n] x[b][k]: grid (K/128, N), fixed summation order over b (deterministic)
-__global__ void __launch_bounds__(128)
+// dW[n][k] = sum_b dy[b][n] x[b][k]: block = 32 k-columns x 8 batch lanes, fixed-order smem combine
+__global__ void __launch_bounds__(256)
 k_fc_wgrad(const float *__restrict__ x, const float *__restrict__ dy, float *__restrict__ dw, float *__restrict__ db,
            int B, int K, int N) {
-    const int kk = blockIdx.x * 128 + threadIdx.x, n = blockIdx.y;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int kk = blockIdx.x * 32 + tx, n = blockIdx.y;
     float s = 0.f, sb = 0.f;
-    if (kk < K)
-        for (int b = 0; b < B; ++b) { float d = dy[(int64_t)b * N + n]; s = fmaf(d, x[(int64_t)b * K + kk], s); sb += d; }
-    if (kk < K) dw[(int64_t)n * K + kk] = s;
-    if (db && kk == 0) db[n] = sb;
+    if (kk < K) {
+        int b = ty;
+        for (; b + 24 < B; b += 32) {
+            float d0 = dy[(int64_t)b * N + n], d1 = dy[(int64_t)(b + 8) * N + n], d2 = dy[(int64_t)(b + 16) * N + n], d3 = dy[(int64_t)(b + 24) * N + n];
+            float x0 = x[(int64_t)b * K + kk], x1 = x[(int64_t)(b + 8) * K + kk], x2 = x[(int64_t)(b + 16) * K + kk], x3 = x[(int64_t)(b + 24) * K + kk];
+            s = fmaf(d0, x0, s); s = fmaf(d1, x1, s); s = fmaf(d2, x2, s); s = fmaf(d3, x3, s);
+            sb += d0 + d1 + d2 + d3;
+        }
+        for (; b < B; b += 8) { float d = dy[(int64_t)b * N + n]; s = fmaf(d, x[(int64_t)b * K + kk], s); sb += d; }
+    }
+    __shared__ float sh[8][33], shb[8];
+    sh[ty][tx] = s;
+    if (tx == 0) shb[ty] = sb;
+    __syncthreads();
+    if (ty == 0 && kk < K) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a += sh[j][tx];
+        dw[(int64_t)n * K + kk] = a;
+        if (db && kk == 0) { float t = 0.f; for (int j = 0; j < 8; ++j) t += shb[j]; db[n] = t; }
+    }
 }
 __global__ void __launch_bounds__(256)
 k_fc_dgrad(const float *__restrict__ w, const float *__restrict__ dy, float *__restrict__ dx, int B, int K, int N, bool acc) {
@@ -677,9 +702,176 @@ k_fc_dgrad(const float *__restrict__ w, const float *__restrict__ dy, float *__r
 }
 int op_fc_backward(const float *x, const float *w, const float *dy, float *dw, float *db, float *dx, int B, int K, int N,
                    bool acc_dx, cudaStream_t s) {
-    dim3 grid((unsigned)ceil_div(K, 128), (unsigned)N);
-    B2_LAUNCH(k_fc_wgrad, grid, 128, 0, s, x, dy, dw, db, B, K, N);
+    dim3 grid((unsigned)ceil_div(K, 32), (unsigned)N);
+    B2_LAUNCH(k_fc_wgrad, grid, 256, 0, s, x, dy, dw, db, B, K, N);
     if (dx) B2_LAUNCH(k_fc_dgrad, grid_for2((int64_t)B * K, 256), 256, 0, s, w, dy, dx, B, K, N, acc_dx);
+    return 0;
+}
+
+}  // namespace b2
+
+// =====================================================================================
+// fused BatchNorm (statistics produced by the conv epilogue)
+// =====================================================================================
+namespace b2 {
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+k_bn_apply_fused(const T *__restrict__ x, T *__restrict__ y, const T *__restrict__ res, const float *__restrict__ fsum,
+                 int64_t M, const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ save_mean,
+                 float *__restrict__ save_invstd, float *running_mean, float *running_var, float eps, float momentum,
+                 bool relu, int64_t total, int C) {
+    extern __shared__ float sm[];             // scale[C], shift[C]
+    float *scale = sm, *shift = sm + C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double mu = (double)fsum[c] / (double)M;
+        double var = (double)fsum[C + c] / (double)M - mu * mu;
+        if (var < 0.0) var = 0.0;
+        float is = (float)(1.0 / sqrt(var + (double)eps));
+        float g = gamma[c];
+        scale[c] = is * g;
+        shift[c] = beta[c] - (float)mu * is * g;
+        if (blockIdx.x == 0) {
+            save_mean[c] = (float)mu; save_invstd[c] = is;
+            if (running_mean) {
+                double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+            }
+        }
+    }
+    __syncthreads();
+    for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * V; i < total; i += (int64_t)gridDim.x * blockDim.x * V) {
+        int c0 = i % C;
+        __align__(16) T xv[V], rv[V], ov[V];
+        *(uint4 *)xv = *(const uint4 *)(x + i);
+        if (res) *(uint4 *)rv = *(const uint4 *)(res + i);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float v = fmaf(to_f<T>(xv[j]), scale[c0 + j], shift[c0 + j]);
+            if (res) v += to_f<T>(rv[j]);
+            if (relu) v = v > 0.f ? v : 0.f;
+            ov[j] = from_f<T>(v);
+        }
+        *(uint4 *)(y + i) = *(uint4 *)ov;
+    }
+}
+
+int op_bn_forward_fused(const void *x, void *y, const void *res, int dt, int64_t M, int C, const float *fsum,
+                        const float *gamma, const float *beta, float *running_mean, float *running_var, float eps,
+                        float momentum, bool relu, const BnWork &w, cudaStream_t s) {
+    B2_CHECK(dt == DT_BF16 && C % 8 == 0, B2_ERR_ARG, "bn fused: bf16 activations with C %% 8 == 0 only");
+    int64_t total = M * C;
+    int64_t blocks = ceil_div(total / 8, 256); if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    B2_LAUNCH((k_bn_apply_fused<bf16, 8>), (int)blocks, 256, 2 * C * sizeof(float), s, (const bf16 *)x, (bf16 *)y, (const bf16 *)res,
+              fsum, M, gamma, beta, w.mean, w.invstd, running_mean, running_var, eps, momentum, relu, total, C);
+    return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_bn_bwd_reduce_atomic(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy,
+                       const float *__restrict__ mean, const float *__restrict__ invstd, bool relu, int64_t M, int C,
+                       int opb /* channel octets per block: min(C/8, 32) */, float *__restrict__ bsum) {
+    // each thread owns 8 consecutive channels (16-byte loads); 256/opb row lanes per block
+    const int tx = threadIdx.x % opb, ty = threadIdx.x / opb, lanes = 256 / opb;
+    const int c0 = (blockIdx.x * opb + tx) * 8;
+    const int64_t rows_per_block = (M + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = blockIdx.y * rows_per_block;
+    int64_t r1 = r0 + rows_per_block; if (r1 > M) r1 = M;
+    float s0[8], s1[8], mu[8], is[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s0[e] = 0.f; s1[e] = 0.f; mu[e] = mean[c0 + e]; is[e] = invstd[c0 + e]; }
+    for (int64_t r = r0 + ty; r < r1; r += lanes) {
+        __align__(16) T xv[8], yv[8], gv[8];
+        *(uint4 *)xv = *(const uint4 *)(x + r * C + c0);
+        *(uint4 *)gv = *(const uint4 *)(dy + r * C + c0);
+        if (relu) *(uint4 *)yv = *(const uint4 *)(y + r * C + c0);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float g = to_f<T>(gv[e]);
+            if (relu && !(to_f<T>(yv[e]) > 0.f)) g = 0.f;
+            s0[e] += g; s1[e] += g * ((to_f<T>(xv[e]) - mu[e]) * is[e]);
+        }
+    }
+    __shared__ float sh[256 * 17];
+    float *mine = sh + threadIdx.x * 17;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { mine[e] = s0[e]; mine[8 + e] = s1[e]; }
+    __syncthreads();
+    if (ty == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float a = 0.f, b = 0.f;
+            for (int j = 0; j < lanes; ++j) { a += sh[(j * opb + tx) * 17 + e]; b += sh[(j * opb + tx) * 17 + 8 + e]; }
+            atomicAdd(bsum + c0 + e, a);
+            atomicAdd(bsum + C + c0 + e, b);
+        }
+    }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+k_bn_bwd_apply_fused(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy, T *__restrict__ dx,
+                     T *__restrict__ dres, const float *__restrict__ mean, const float *__restrict__ invstd,
+                     const float *__restrict__ bsum, const float *__restrict__ gamma, float *__restrict__ dgamma,
+                     float *__restrict__ dbeta, int64_t M, bool relu, bool acc_dx, bool acc_dres, int64_t total, int C) {
+    extern __shared__ float sm[];     // a[C], b[C], k[C]: dx = a*g + b*x + k   (per channel)
+    float *ca = sm, *cb = sm + C, *ck = sm + 2 * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float sg = bsum[c], sgx = bsum[C + c];
+        float is = invstd[c], mu = mean[c], a = gamma[c] * is;
+        float c1 = sg / (float)M, c2 = sgx / (float)M;
+        // dx = a*(g - c1 - xhat*c2), xhat = (x - mu)*is
+        ca[c] = a; cb[c] = -a * c2 * is; ck[c] = -a * c1 + a * c2 * is * mu;
+        if (blockIdx.x == 0) { dbeta[c] = sg; dgamma[c] = sgx; }
+    }
+    __syncthreads();
+    for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * V; i < total; i += (int64_t)gridDim.x * blockDim.x * V) {
+        int c0 = i % C;
+        __align__(16) T xv[V], yv[V], gv[V], ov[V], rv[V], pv[V];
+        *(uint4 *)xv = *(const uint4 *)(x + i);
+        *(uint4 *)gv = *(const uint4 *)(dy + i);
+        if (relu) *(uint4 *)yv = *(const uint4 *)(y + i);
+        if (acc_dx) *(uint4 *)pv = *(const uint4 *)(dx + i);
+        if (dres && acc_dres) *(uint4 *)rv = *(const uint4 *)(dres + i);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            int c = c0 + j;
+            float g = to_f<T>(gv[j]);
+            if (relu && !(to_f<T>(yv[j]) > 0.f)) g = 0.f;
+            float d = fmaf(ca[c], g, fmaf(cb[c], to_f<T>(xv[j]), ck[c]));
+            if (acc_dx) d += to_f<T>(pv[j]);
+            ov[j] = from_f<T>(d);
+            if (dres) {
+                float r = g;
+                if (acc_dres) r += to_f<T>(rv[j]);
+                rv[j] = from_f<T>(r);
+            }
+        }
+        *(uint4 *)(dx + i) = *(uint4 *)ov;
+        if (dres) *(uint4 *)(dres + i) = *(uint4 *)rv;
+    }
+}
+
+int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx, void *dres, int dt, int64_t M, int C,
+                         float *bsum, const float *gamma, float *dgamma, float *dbeta, bool relu, bool acc_dx,
+                         bool acc_dres, const BnWork &w, cudaStream_t s) {
+    B2_CHECK(dt == DT_BF16 && C % 8 == 0, B2_ERR_ARG, "bn fused: bf16 activations with C %% 8 == 0 only");
+    int opb = C / 8 < 32 ? C / 8 : 32;
+    B2_CHECK((C / 8) % opb == 0 && 256 % opb == 0, B2_ERR_ARG, "bn fused: unsupported channel count %d", C);
+    int gx = (C / 8) / opb;
+    int lanes = 256 / opb;
+    int64_t want = (kNumSMs * 4 + gx - 1) / gx;
+    int64_t maxb = ceil_div(M, (int64_t)lanes * 2); if (want > maxb) want = maxb; if (want < 1) want = 1;
+    dim3 grid(gx, (unsigned)want);
+    B2_LAUNCH((k_bn_bwd_reduce_atomic<bf16>), grid, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, w.mean, w.invstd,
+              relu, M, C, opb, bsum);
+    int64_t total = M * C;
+    int64_t blocks = ceil_div(total / 8, 256); if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    B2_LAUNCH((k_bn_bwd_apply_fused<bf16, 8>), (int)blocks, 256, 3 * C * sizeof(float), s, (const bf16 *)x, (const bf16 *)y,
+              (const bf16 *)dy, (bf16 *)dx, (bf16 *)dres, w.mean, w.invstd, bsum, gamma, dgamma, dbeta, M, relu, acc_dx, acc_dres,
+              total, C);
     return 0;
 }
 
