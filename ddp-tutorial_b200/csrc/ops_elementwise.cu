@@ -583,38 +583,43 @@ int op_maxpool_backward_bf16x8(const bf16 *dy, const uint8_t *idx, bf16 *dx, int
     return 0;
 }
 
-// ---- stem im2col: one thread per (output pixel, 8 consecutive columns) -> one 16-byte store
+// ---- stem im2col: one thread per (output pixel, 8 consecutive columns) -> one 16-byte store.
+// KS / CH are compile-time so the (kh, kw, c) decode is multiply-shift, not integer division.
+template <int KS, int CH>
 __global__ void __launch_bounds__(256)
-k_stem_im2col(const float *__restrict__ x, bf16 *__restrict__ col, int N, int C, int H, int W, int k, int stride, int pad,
+k_stem_im2col(const float *__restrict__ x, bf16 *__restrict__ col, int N, int H, int W, int stride, int pad,
               int Ho, int Wo, int kpad) {
     const int chunks = kpad >> 3;
-    const int K = k * k * C;
+    constexpr int K = KS * KS * CH;
     const int64_t total = (int64_t)N * Ho * Wo * chunks;
+    const int HoWo = Ho * Wo;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int ch = i % chunks; int64_t m = i / chunks;
-        int wo = m % Wo; int64_t t = m / Wo;
-        int ho = t % Ho; int n = (int)(t / Ho);
+        const int ch = (int)(i % chunks); const int m = (int)(i / chunks);
+        const int n = m / HoWo; const int rem = m - n * HoWo;
+        const int ho = rem / Wo, wo = rem - ho * Wo;
+        const float *xn = x + (int64_t)n * CH * H * W;
         __align__(16) bf16 o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            int kk = ch * 8 + e;
+            const int kk = ch * 8 + e;
             float v = 0.f;
             if (kk < K) {
-                int c = kk % C; int tap = kk / C;
-                int kw = tap % k, kh = tap / k;
-                int hi = ho * stride - pad + kh, wi = wo * stride - pad + kw;
-                if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = __ldg(x + (((int64_t)n * C + c) * H + hi) * W + wi);
+                const int tap = kk / CH, c = kk - tap * CH;
+                const int kh = tap / KS, kw = tap - kh * KS;
+                const int hi = ho * stride - pad + kh, wi = wo * stride - pad + kw;
+                if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = __ldg(xn + ((int64_t)c * H + hi) * W + wi);
             }
             o[e] = __float2bfloat16_rn(v);
         }
-        *(uint4 *)(col + m * kpad + ch * 8) = *(uint4 *)o;
+        *(uint4 *)(col + (int64_t)m * kpad + ch * 8) = *(uint4 *)o;
     }
 }
 int op_stem_im2col(const float *x_nchw, bf16 *col, int N, int C, int H, int W, int k, int stride, int pad, int Ho, int Wo,
                    int kpad, cudaStream_t s) {
     B2_CHECK(kpad % 8 == 0 && kpad >= k * k * C, B2_ERR_ARG, "stem im2col: bad kpad %d", kpad);
+    B2_CHECK(k == 7 && C == 3, B2_ERR_UNSUPPORTED, "stem im2col: only the 7x7 / 3-channel ResNet stem is instantiated");
     int64_t total = (int64_t)N * Ho * Wo * (kpad / 8);
-    B2_LAUNCH(k_stem_im2col, grid_for2(total, 256), 256, 0, s, x_nchw, col, N, C, H, W, k, stride, pad, Ho, Wo, kpad);
+    B2_LAUNCH((k_stem_im2col<7, 3>), grid_for2(total, 256), 256, 0, s, x_nchw, col, N, H, W, stride, pad, Ho, Wo, kpad);
     return 0;
 }
 
@@ -634,30 +639,28 @@ int op_copy_2d_f32(const float *src, int spitch, float *dst, int dpitch, int row
 __global__ void __launch_bounds__(256)
 k_fc_fwd(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias, float *__restrict__ y,
          int B, int K, int N, bool relu) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= B) return;
-    const float *xr = x + (int64_t)warp * K;
-    float acc[32];
-#pragma unroll
-    for (int n = 0; n < 32; ++n) acc[n] = 0.f;
-    for (int kk = lane; kk < K; kk += 32) {
-        const float xv = xr[kk];
-#pragma unroll
-        for (int n = 0; n < 32; ++n) if (n < N) acc[n] = fmaf(xv, __ldg(w + (int64_t)n * K + kk), acc[n]);
-    }
-#pragma unroll
-    for (int n = 0; n < 32; ++n) {
-        if (n >= N) break;
-        float s = warp_sum(acc[n]);
-        if (lane == 0) {
-            if (bias) s += bias[n];
-            if (relu) s = s > 0.f ? s : 0.f;
-            y[(int64_t)warp * N + n] = s;
+    // one thread per output (b, n); K-loop with 4 independent accumulators
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * N) return;
+    const int n = (int)(i % N); const int64_t b = i / N;
+    const float *xr = x + b * K, *wr = w + (int64_t)n * K;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int kk = 0;
+    if ((K & 3) == 0) {
+        for (; kk < K; kk += 4) {
+            float4 xv = *(const float4 *)(xr + kk), wv = *(const float4 *)(wr + kk);
+            a0 = fmaf(xv.x, wv.x, a0); a1 = fmaf(xv.y, wv.y, a1); a2 = fmaf(xv.z, wv.z, a2); a3 = fmaf(xv.w, wv.w, a3);
         }
+    } else {
+        for (; kk < K; ++kk) a0 = fmaf(xr[kk], wr[kk], a0);
     }
+    float s = (a0 + a1) + (a2 + a3);
+    if (bias) s += bias[n];
+    if (relu) s = s > 0.f ? s : 0.f;
+    y[i] = s;
 }
 int op_fc_forward(const float *x, const float *w, const float *bias, float *y, int B, int K, int N, bool relu, cudaStream_t s) {
-    B2_LAUNCH(k_fc_fwd, (int)ceil_div((int64_t)B * 32, 256), 256, 0, s, x, w, bias, y, B, K, N, relu);
+    B2_LAUNCH(k_fc_fwd, (int)ceil_div((int64_t)B * N, 128), 128, 0, s, x, w, bias, y, B, K, N, relu);
     return 0;
 }
 // dW[n][k] = sum_b dy[b][n] x[b][k]: block = 32 k-columns x 8 batch lanes, fixed-order smem combine
@@ -795,17 +798,23 @@ k_bn_bwd_reduce_atomic(const T *__restrict__ x, const T *__restrict__ y, const T
         }
     }
     __shared__ float sh[256 * 17];
-    float *mine = sh + threadIdx.x * 17;
+    float *mine = sh + threadIdx.x * 17;       // thread (ty, tx) sits at index ty*opb + tx == threadIdx.x
 #pragma unroll
     for (int e = 0; e < 8; ++e) { mine[e] = s0[e]; mine[8 + e] = s1[e]; }
     __syncthreads();
+    for (int stride = lanes >> 1; stride > 0; stride >>= 1) {      // tree over the row lanes, all threads busy
+        if (ty < stride) {
+            const float *other = sh + (threadIdx.x + stride * opb) * 17;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) mine[e] += other[e];
+        }
+        __syncthreads();
+    }
     if (ty == 0) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            float a = 0.f, b = 0.f;
-            for (int j = 0; j < lanes; ++j) { a += sh[(j * opb + tx) * 17 + e]; b += sh[(j * opb + tx) * 17 + 8 + e]; }
-            atomicAdd(bsum + c0 + e, a);
-            atomicAdd(bsum + C + c0 + e, b);
+            atomicAdd(bsum + c0 + e, mine[e]);
+            atomicAdd(bsum + C + c0 + e, mine[8 + e]);
         }
     }
 }
@@ -862,8 +871,8 @@ int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx,
     B2_CHECK((C / 8) % opb == 0 && 256 % opb == 0, B2_ERR_ARG, "bn fused: unsupported channel count %d", C);
     int gx = (C / 8) / opb;
     int lanes = 256 / opb;
-    int64_t want = (kNumSMs * 4 + gx - 1) / gx;
-    int64_t maxb = ceil_div(M, (int64_t)lanes * 2); if (want > maxb) want = maxb; if (want < 1) want = 1;
+    int64_t want = (kNumSMs * 2 + gx - 1) / gx;
+    int64_t maxb = ceil_div(M, (int64_t)lanes * 4); if (want > maxb) want = maxb; if (want < 1) want = 1;
     dim3 grid(gx, (unsigned)want);
     B2_LAUNCH((k_bn_bwd_reduce_atomic<bf16>), grid, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, w.mean, w.invstd,
               relu, M, C, opb, bsum);
