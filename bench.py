@@ -215,10 +215,9 @@ def run_b2(args):
     sampler = ClockSampler(dev) if (rank == 0 and not args.no_clocks) else None   # nvidia-smi needs ~1 s to start
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    if sampler is not None:
-        t_end = time.time() + 1.5
-        while time.time() < t_end:                           # keep the GPU under load until samples flow
-            step_resident()
+    if not args.no_clocks:
+        for _ in range(800):                                 # ~1 s under load on EVERY rank (same collective count)
+            step_resident()                                  # so that nvidia-smi samples flow before the timed region
     launches0 = b2.lib().b2_launch_count()
     ms, last = timed(step_resident, args.steps)
     launches = b2.lib().b2_launch_count() - launches0
@@ -230,7 +229,7 @@ def run_b2(args):
 
     # ---- roofline leg: events around every op of the dominant kernel class (separate pass)
     roofline = None
-    if rank == 0:
+    if True:                                                 # every rank runs the same steps (collectives must match)
         e = net.engine
         m = e._model(BATCH)
         b2._lib.call("b2_model_profile", m.h, 1)
