@@ -62,8 +62,11 @@ _SIGS = {
     "b2_comm_check": (_i, []),
     "b2_allreduce": (_i, [_i64, _f, _i, _vp]),
     "b2_allreduce_range": (_i, [_i64, _i64, _f, _i, _vp]),
-    "b2_allreduce_sgd": (_i, [_vp, _i64, _f, _f, _i, _i, _vp]),
-    "b2_allreduce_sgd_range": (_i, [_vp, _i64, _i64, _f, _f, _i, _i, _vp]),
+    "b2_allreduce_sgd": (_i, [_vp, _i64, _f, _f, _i, _i, _vp, _vp]),
+    "b2_allreduce_sgd_range": (_i, [_vp, _i64, _i64, _f, _f, _i, _i, _vp, _vp]),
+    "b2_model_set_ddp": (_i, [_vp, _i, _vp, _f, _f, _i, _i64]),
+    "b2_model_ddp_first_step": (_i, [_vp, _i]),
+    "b2_model_num_buckets": (_i, [_vp]),
     "b2_graph_begin": (_i, [_vp]),
     "b2_graph_end": (_i, [_vp, C.POINTER(_vp)]),
     "b2_graph_launch": (_i, [_vp, _vp]),

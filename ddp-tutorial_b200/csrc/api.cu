@@ -124,6 +124,18 @@ int b2_model_set_graphs(b2_model *h, int enable) {
     if (!enable) h->m->drop_graphs();
     return 0;
 }
+int b2_model_set_ddp(b2_model *h, int enable, float *momentum_buf, float lr, float momentum, int algo, int64_t bucket_elems) {
+    GUARD_BEGIN
+    B2_CHECK(h, B2_ERR_ARG, "NULL model");
+    return h->m->set_ddp(enable != 0, momentum_buf, lr, momentum, algo, bucket_elems);
+    GUARD_END
+}
+int b2_model_ddp_first_step(b2_model *h, int first) {
+    B2_CHECK(h, B2_ERR_ARG, "NULL model");
+    if (h->m->ddp_first != (first ? 1 : 0)) { h->m->ddp_first = first ? 1 : 0; h->m->drop_graphs(); h->m->eager_runs_bwd = 0; }
+    return 0;
+}
+int b2_model_num_buckets(const b2_model *h) { return h ? (int)h->m->buckets.size() : 0; }
 int b2_model_profile(b2_model *h, int enable) {
     B2_CHECK(h, B2_ERR_ARG, "NULL model");
     h->m->profiling = enable != 0;

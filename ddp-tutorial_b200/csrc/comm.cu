@@ -22,7 +22,7 @@
 namespace b2 {
 
 constexpr int kMaxWorld = 8;
-constexpr int kCommBlocks = 64;       // blocks per comm kernel (all co-resident; same on every rank)
+constexpr int kCommBlocks = 96;       // blocks per comm kernel (all co-resident; same on every rank)
 constexpr int kCommThreads = 512;
 // flag layout (uint32 words): [phase 0/1][src rank][block]
 constexpr int kFlagStride = kCommBlocks;
@@ -90,6 +90,11 @@ __device__ __forceinline__ void peer_barrier(const CommPtrs &P, int rank, uint32
     __syncthreads();
 }
 
+__device__ __forceinline__ void st_bf16x4(bf16 *dst, float4 v) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk; pk.x = *(uint32_t *)&lo; pk.y = *(uint32_t *)&hi;
+    *(uint2 *)dst = pk;
+}
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 
@@ -107,7 +112,7 @@ __device__ __forceinline__ void sgd_apply(float4 &p, float4 &m, const float4 g, 
 template <int W, int MODE, bool ONESHOT>
 __global__ void __launch_bounds__(kCommThreads)
 k_allreduce(const CommPtrs P, int rank, float *__restrict__ mom_buf, int64_t off, int64_t n4 /* float4 count */,
-            float scale, float lr, float momentum, int first, uint32_t *epoch_mem, int *err) {
+            float scale, float lr, float momentum, int first, bf16 *__restrict__ mirror, uint32_t *epoch_mem, int *err) {
     peer_barrier<W>(P, rank, epoch_mem, 0, err);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -123,6 +128,7 @@ k_allreduce(const CommPtrs P, int rank, float *__restrict__ mom_buf, int64_t off
                 sgd_apply(p, m, acc, lr, momentum, first);
                 *(float4 *)(mom_buf + e) = m;
                 *(float4 *)(P.params[rank] + e) = p;
+                if (mirror) st_bf16x4(mirror + e, p);
             }
             peer_barrier<W>(P, rank, epoch_mem, 1, err);      // peers are done reading my grads
         } else {
@@ -143,11 +149,15 @@ k_allreduce(const CommPtrs P, int rank, float *__restrict__ mom_buf, int64_t off
         const int64_t per = (n4 + W - 1) / W;
         const int64_t lo = (int64_t)rank * per;
         int64_t hi = lo + per; if (hi > n4) hi = n4;
+#pragma unroll 2
         for (int64_t i = lo + tid; i < hi; i += stride) {
             const int64_t e = off + i * 4;
-            float4 acc = ld_peer_f4(P.grads[0] + e);
+            float4 part[W];
 #pragma unroll
-            for (int r = 1; r < W; ++r) acc = f4_add(acc, ld_peer_f4(P.grads[r] + e));
+            for (int r = 0; r < W; ++r) part[r] = ld_peer_f4(P.grads[r] + e);     // all W loads in flight
+            float4 acc = part[0];
+#pragma unroll
+            for (int r = 1; r < W; ++r) acc = f4_add(acc, part[r]);
             acc = f4_scale(acc, scale);
             if (MODE == 1) {
                 float4 p = *(float4 *)(P.params[rank] + e), m = first ? acc : *(float4 *)(mom_buf + e);
@@ -161,6 +171,13 @@ k_allreduce(const CommPtrs P, int rank, float *__restrict__ mom_buf, int64_t off
             }
         }
         peer_barrier<W>(P, rank, epoch_mem, 1, err);          // all slices have landed everywhere
+        if (MODE == 1 && mirror) {
+            // every replica now holds the full updated fp32 range: refresh the local bf16 mirror
+            for (int64_t i = tid; i < n4; i += stride) {
+                const int64_t e = off + i * 4;
+                st_bf16x4(mirror + e, ld_peer_f4(P.params[rank] + e));
+            }
+        }
     }
 }
 
@@ -173,7 +190,7 @@ k_barrier_only(const CommPtrs P, int rank, uint32_t *epoch_mem, int *err) {
 
 template <int MODE>
 static int launch_allreduce(int64_t off, int64_t n, float *m, float scale, float lr, float momentum, int first,
-                            int algo, cudaStream_t s) {
+                            int algo, bf16 *mirror, cudaStream_t s) {
     CommState &c = g_comm;
     B2_CHECK(c.inited && c.registered, B2_ERR_STATE, "comm: not initialised / no buffers registered");
     B2_CHECK(off >= 0 && n >= 0 && off + n <= c.n_elems, B2_ERR_ARG, "comm: range [%lld,+%lld) outside registered %lld",
@@ -191,9 +208,9 @@ static int launch_allreduce(int64_t off, int64_t n, float *m, float scale, float
     if (c.world == 1) oneshot = true;
 #define LAUNCH_W(Wv)                                                                                              \
     if (oneshot) { B2_LAUNCH((k_allreduce<Wv, MODE, true>), kCommBlocks, kCommThreads, 0, s, c.ptrs, c.rank, m, off, n4, \
-                             scale, lr, momentum, first, c.epoch, c.err); }                                           \
+                             scale, lr, momentum, first, mirror, c.epoch, c.err); }                                   \
     else { B2_LAUNCH((k_allreduce<Wv, MODE, false>), kCommBlocks, kCommThreads, 0, s, c.ptrs, c.rank, m, off, n4, scale,   \
-                     lr, momentum, first, c.epoch, c.err); }
+                     lr, momentum, first, mirror, c.epoch, c.err); }
     switch (c.world) {
     case 1: LAUNCH_W(1); break;
     case 2: LAUNCH_W(2); break;
@@ -204,6 +221,14 @@ static int launch_allreduce(int64_t off, int64_t n, float *m, float scale, float
 #undef LAUNCH_W
     return 0;
 }
+
+// entry for the model's bucketed backward (model.cu)
+int comm_allreduce_sgd_range(float *m, int64_t off, int64_t n, float lr, float momentum, int first, int algo, bf16 *mirror,
+                             cudaStream_t s) {
+    B2_CHECK(g_comm.inited && g_comm.ptrs.params[0] != nullptr, B2_ERR_STATE, "allreduce_sgd: communicator has no parameter buffers");
+    return launch_allreduce<1>(off, n, m, 1.f / (float)g_comm.world, lr, momentum, first, algo, mirror, s);
+}
+bool comm_ready() { return g_comm.inited && g_comm.registered; }
 
 }  // namespace b2
 
@@ -316,22 +341,21 @@ int b2_comm_barrier(void *stream) {
 }
 
 int b2_allreduce(int64_t n_elems, float scale, int algo, void *stream) {
-    return launch_allreduce<0>(0, n_elems, nullptr, scale, 0.f, 0.f, 0, algo, (cudaStream_t)stream);
+    return launch_allreduce<0>(0, n_elems, nullptr, scale, 0.f, 0.f, 0, algo, nullptr, (cudaStream_t)stream);
 }
 int b2_allreduce_range(int64_t offset, int64_t n_elems, float scale, int algo, void *stream) {
-    return launch_allreduce<0>(offset, n_elems, nullptr, scale, 0.f, 0.f, 0, algo, (cudaStream_t)stream);
+    return launch_allreduce<0>(offset, n_elems, nullptr, scale, 0.f, 0.f, 0, algo, nullptr, (cudaStream_t)stream);
 }
 
-int b2_allreduce_sgd(float *m, int64_t n_elems, float lr, float momentum, int first_step, int algo, void *stream) {
+int b2_allreduce_sgd(float *m, int64_t n_elems, float lr, float momentum, int first_step, int algo, void *p_bf16,
+                     void *stream) {
     B2_CHECK(m, B2_ERR_ARG, "allreduce_sgd: NULL momentum buffer");
-    B2_CHECK(g_comm.ptrs.params[0] != nullptr, B2_ERR_STATE, "allreduce_sgd: no parameter buffers registered");
-    return launch_allreduce<1>(0, n_elems, m, 1.f / (float)g_comm.world, lr, momentum, first_step, algo, (cudaStream_t)stream);
+    return comm_allreduce_sgd_range(m, 0, n_elems, lr, momentum, first_step, algo, (bf16 *)p_bf16, (cudaStream_t)stream);
 }
 int b2_allreduce_sgd_range(float *m, int64_t offset, int64_t n_elems, float lr, float momentum, int first_step, int algo,
-                           void *stream) {
+                           void *p_bf16, void *stream) {
     B2_CHECK(m, B2_ERR_ARG, "allreduce_sgd: NULL momentum buffer");
-    B2_CHECK(g_comm.ptrs.params[0] != nullptr, B2_ERR_STATE, "allreduce_sgd: no parameter buffers registered");
-    return launch_allreduce<1>(offset, n_elems, m, 1.f / (float)g_comm.world, lr, momentum, first_step, algo, (cudaStream_t)stream);
+    return comm_allreduce_sgd_range(m, offset, n_elems, lr, momentum, first_step, algo, (bf16 *)p_bf16, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -301,8 +301,57 @@ bool Model::ops_produce(int tensor) const {
     return false;
 }
 
+// params each op produces gradients for, as (offset, padded length) in the flat vector
+static void op_param_ranges(const Model &m, const Op &o, std::vector<std::pair<int64_t, int64_t>> &out) {
+    auto find = [&](int64_t off) {
+        for (const ParamInfo &p : m.params) if (p.offset == off) { out.push_back({p.offset, (p.numel + 63) / 64 * 64}); return; }
+    };
+    if (o.type == OP_CONV) { find(o.w_off); if (o.b_off >= 0) find(o.b_off); }
+    else if (o.type == OP_BN) { find(o.w_off); find(o.b_off); }
+}
+
+void Model::compute_buckets(int64_t bucket_elems) {
+    buckets.clear();
+    std::vector<char> done(params.size(), 0);
+    int64_t suffix = n_params;           // everything at offsets >= suffix has its gradient
+    int64_t emitted = n_params;
+    for (int i = (int)ops.size() - 1; i >= 0; --i) {
+        std::vector<std::pair<int64_t, int64_t>> r;
+        op_param_ranges(*this, ops[i], r);
+        for (auto &pr : r)
+            for (size_t k = 0; k < params.size(); ++k) if (params[k].offset == pr.first) done[k] = 1;
+        // largest complete suffix (params are stored in ascending offset order)
+        suffix = n_params;
+        for (int k = (int)params.size() - 1; k >= 0 && done[k]; --k) suffix = params[k].offset;
+        if (emitted - suffix >= bucket_elems || (i == 0 && emitted > suffix)) {
+            buckets.push_back(Bucket{suffix, emitted - suffix, i});
+            emitted = suffix;
+        }
+    }
+    if (emitted > 0) buckets.push_back(Bucket{0, emitted, 0});
+}
+
+int Model::set_ddp(bool enable, float *mom, float lr, float momentum, int algo, int64_t bucket_elems) {
+    drop_graphs();
+    eager_runs_bwd = 0;
+    ddp_on = false;
+    if (!enable) return 0;
+    B2_CHECK(comm_ready(), B2_ERR_STATE, "set_ddp: communicator not initialised / no buffers registered");
+    B2_CHECK(mom, B2_ERR_ARG, "set_ddp: NULL momentum buffer");
+    ddp_mom = mom; ddp_lr = lr; ddp_momentum = momentum; ddp_algo = algo;
+    if (!ddp_stream) {
+        B2_CUDA(cudaStreamCreateWithFlags(&ddp_stream, cudaStreamNonBlocking));
+        B2_CUDA(cudaEventCreateWithFlags(&ddp_fork, cudaEventDisableTiming));
+        B2_CUDA(cudaEventCreateWithFlags(&ddp_join, cudaEventDisableTiming));
+    }
+    compute_buckets(bucket_elems > 0 ? bucket_elems : (int64_t)2 << 20);
+    ddp_on = true;
+    return 0;
+}
+
 Model::~Model() {
     drop_graphs();
+    if (ddp_stream) { cudaStreamDestroy(ddp_stream); cudaEventDestroy(ddp_fork); cudaEventDestroy(ddp_join); }
     if (cap_stream) cudaStreamDestroy(cap_stream);
     if (slab) cudaFree(slab);
 }
@@ -519,9 +568,23 @@ int Model::backward(const float *dlogits, cudaStream_t s) {
 int Model::backward_impl(const float *dlogits, cudaStream_t s) {
     Tensor &tl = tensors[logits_tensor];
     B2_CUDA(cudaMemcpyAsync(tl.grad, dlogits, tl.numel * 4, cudaMemcpyDeviceToDevice, s));
+    size_t next_bucket = 0;
+    bool forked = false;
+    auto flush_buckets = [&](int i) -> int {
+        // every bucket whose last gradient was produced by ops[i]: exchange + apply on the side stream
+        while (ddp_on && next_bucket < buckets.size() && buckets[next_bucket].after_op >= i) {
+            const Bucket &bk = buckets[next_bucket++];
+            B2_CUDA(cudaEventRecord(ddp_fork, s));
+            B2_CUDA(cudaStreamWaitEvent(ddp_stream, ddp_fork, 0));
+            B2_TRY(comm_allreduce_sgd_range(ddp_mom, bk.off, bk.n, ddp_lr, ddp_momentum, ddp_first, ddp_algo,
+                                            p_params_bf16, ddp_stream));
+            forked = true;
+        }
+        return 0;
+    };
     for (int i = (int)ops.size() - 1; i >= 0; --i) {
         Op &o = ops[i];
-        if (o.type == OP_INPUT) continue;
+        if (o.type == OP_INPUT) { B2_TRY(flush_buckets(i)); continue; }
         Tensor &to = tensors[o.out];
         Tensor &ti = tensors[o.in];
         switch (o.type) {
@@ -592,9 +655,15 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
             B2_TRY(op_avgpool_backward((const float *)to.grad, ti.grad, ti.dt, ti.N, ti.H * ti.W, ti.C, o.acc_in, s));
             break;
         }
+        B2_TRY(flush_buckets(i));
+    }
+    if (forked) {                                   // join: the caller's stream continues after the exchange
+        B2_CUDA(cudaEventRecord(ddp_join, ddp_stream));
+        B2_CUDA(cudaStreamWaitEvent(s, ddp_join, 0));
     }
     return 0;
 }
+
 
 int Model::create(int kind, int batch, int num_classes, int precision, int device, Model **out) {
     B2_CHECK(batch > 0 && num_classes > 0, B2_ERR_ARG, "model: batch and num_classes must be positive");

@@ -78,6 +78,16 @@ struct Model {
     int backward_impl(const float *dlogits, cudaStream_t s);
     int run_graphed(std::vector<GraphEntry> &cache, const void *a, const void *b, bool is_fwd, cudaStream_t s);
     void drop_graphs();
+    // DDP inside backward: gradient buckets (contiguous suffixes of the flat vector, in the
+    // order backward completes them) exchanged + applied on a side stream while backward runs
+    struct Bucket { int64_t off, n; int after_op; };   // launch after ops[after_op] has run backward
+    std::vector<Bucket> buckets;
+    bool ddp_on = false;
+    float *ddp_mom = nullptr; float ddp_lr = 0.f, ddp_momentum = 0.f; int ddp_algo = 0, ddp_first = 1;
+    cudaStream_t ddp_stream = nullptr;
+    cudaEvent_t ddp_fork = nullptr, ddp_join = nullptr;
+    int set_ddp(bool enable, float *mom, float lr, float momentum, int algo, int64_t bucket_elems);
+    void compute_buckets(int64_t bucket_elems);
     int64_t steps_tracked = 0;
     bool profiling = false;
     std::vector<ProfRec> prof;

@@ -98,4 +98,9 @@ int op_ce_loss_grad(const float *logits, const int64_t *labels, int B, int C, fl
 int op_sgd(float *p, const float *g, float *m, int64_t n, float lr, float momentum, float gscale,
            int first, bf16 *pb, cudaStream_t s);
 
+// ---- communicator hooks used by the model's bucketed backward (comm.cu) ------------------
+bool comm_ready();
+int comm_allreduce_sgd_range(float *m, int64_t off, int64_t n, float lr, float momentum, int first, int algo, bf16 *mirror,
+                             cudaStream_t s);
+
 }  // namespace b2

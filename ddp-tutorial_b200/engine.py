@@ -120,6 +120,8 @@ class Engine:
                 call("b2_model_set_graphs", m.h, 0)
             if self.flat_params is not None:
                 self._bind(m)
+            if self.ddp is not None and self.optimizer is not None and self.ddp.overlap:
+                self.ddp._configure_model(m, self.optimizer)
             self.models[batch] = m
         return m
 
@@ -211,6 +213,8 @@ class Engine:
         if self._last_batch is None:
             raise B2Error("backward() before forward()")
         m = self._model(self._last_batch)
+        if self.ddp is not None:
+            self.ddp._before_backward(m)
         call("b2_backward", m.h, C.c_void_p(dlogits.data_ptr()), _stream_ptr())
         if self.ddp is not None:
             self.ddp._after_backward()

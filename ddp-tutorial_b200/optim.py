@@ -32,6 +32,8 @@ class SGD:
         self.state_steps = 0
         self.momentum_buffer = torch.zeros_like(engine.flat_params)
         engine.optimizer = self
+        if engine.ddp is not None:
+            engine.ddp._attach_optimizer(self)
 
     def zero_grad(self, set_to_none: bool = True):
         """Gradients live in the flat bucket and are fully overwritten by every backward

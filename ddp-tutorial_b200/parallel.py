@@ -105,7 +105,8 @@ class DistributedDataParallel:
     Per step: see ``_optimizer_step``.
     """
 
-    def __init__(self, module, device_ids: Optional[List[int]] = None, algo: int = 0):
+    def __init__(self, module, device_ids: Optional[List[int]] = None, algo: int = 0, overlap: bool = True,
+                 bucket_cap_mb: float = 8.0):
         if not _state["distributed"]:
             raise B2Error("Default process group has not been initialized: call init_distributed(args) "
                           "under torchrun first (cifar_example_ddp.py:69)")
@@ -117,6 +118,14 @@ class DistributedDataParallel:
             raise B2Error(f"device_ids={device_ids} does not match the model's device {e.device}")
         self.engine = e
         self.algo = algo
+        # overlap=True: the fused all-reduce + SGD of each gradient bucket is launched from inside
+        # backward() on a side stream as soon as the bucket is complete (the reference overlaps its
+        # NCCL all-reduce with backward the same way, reducer.hpp:524); parameters are therefore
+        # already updated when backward() returns and optimizer.step() only does bookkeeping.
+        # overlap=False: one fused kernel over the whole vector at optimizer.step().
+        self.overlap = overlap
+        self.bucket_elems = int(bucket_cap_mb * (1 << 20) / 4)
+        self._fused_pending = False
         W, r = _state["world"], _state["rank"]
         dev = e.device
         npad = max((e.n_params + 3) // 4 * 4, 4)
@@ -154,6 +163,26 @@ class DistributedDataParallel:
         _exchange("params-copied")
         e.mark_weights_dirty()
         e.ddp = self
+        if e.optimizer is not None:
+            self._attach_optimizer(e.optimizer)
+
+    def _attach_optimizer(self, opt):
+        """Called when an SGD is built over this model's parameters (cifar_example_ddp.py:86)."""
+        if not self.overlap:
+            return
+        e = self.engine
+        for m in e.models.values():
+            self._configure_model(m, opt)
+
+    def _configure_model(self, m, opt):
+        call("b2_model_set_ddp", m.h, 1, C.c_void_p(opt.momentum_buffer.data_ptr()), opt.lr, opt.momentum, self.algo,
+             self.bucket_elems)
+
+    def _before_backward(self, m):
+        opt = self.engine.optimizer
+        if self.overlap and opt is not None:
+            call("b2_model_ddp_first_step", m.h, 1 if opt.state_steps == 0 else 0)
+            self._fused_pending = True
 
     # -- module surface -------------------------------------------------------------------
     def __call__(self, inputs):
@@ -181,9 +210,18 @@ class DistributedDataParallel:
 
     def _optimizer_step(self, opt, first: int):
         e = self.engine
-        call("b2_allreduce_sgd", C.c_void_p(opt.momentum_buffer.data_ptr()), e.n_params, opt.lr, opt.momentum,
-             first, self.algo, _stream_ptr())
-        e.mark_weights_dirty()
+        mirror = e.flat_params_bf16
+        if self.overlap:
+            if not self._fused_pending:
+                raise B2Error("optimizer.step() without a preceding backward()")
+            self._fused_pending = False            # exchange + update already ran inside backward()
+        else:
+            call("b2_allreduce_sgd", C.c_void_p(opt.momentum_buffer.data_ptr()), e.n_params, opt.lr, opt.momentum,
+                 first, self.algo, C.c_void_p(mirror.data_ptr()) if mirror is not None else None, _stream_ptr())
+        if mirror is not None:
+            e.mark_weights_clean()                 # the same kernel refreshed the local bf16 mirror
+        else:
+            e.mark_weights_dirty()
 
     def allreduce_grads(self):
         """Unfused form (gradients averaged in place on every rank) -- for tests and for users

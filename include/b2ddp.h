@@ -147,7 +147,7 @@ int b2_comm_unimport(void *peer_ptr);
 /* register the per-rank buffers of one "channel": grads[w], params[w] and
  * flags[w] (uint32 signal pads, >= B2_FLAG_WORDS words, zero-initialised) are the
  * world-size arrays of mapped pointers (entry `rank` is the local one). */
-#define B2_FLAG_WORDS 1024
+#define B2_FLAG_WORDS 2048
 int b2_comm_register(void *const *grads, void *const *params, void *const *flags, int64_t n_elems);
 /* dist.barrier() (cifar_example_ddp.py:58): flag barrier in peer memory */
 int b2_comm_barrier(void *stream);
@@ -166,9 +166,19 @@ int b2_allreduce_range(int64_t offset, int64_t n_elems, float scale, int algo, v
  * the registered params (m is local, fp32 [n]): Reducer + optimizer.step() in one
  * kernel (cifar_example_ddp.py:106-107). */
 int b2_allreduce_sgd(float *m, int64_t n_elems, float lr, float momentum, int first_step,
-                     int algo, void *stream);
+                     int algo, void *p_bf16 /* optional local bf16 mirror */, void *stream);
 int b2_allreduce_sgd_range(float *m, int64_t offset, int64_t n_elems, float lr, float momentum,
-                           int first_step, int algo, void *stream);
+                           int first_step, int algo, void *p_bf16, void *stream);
+/* DDP inside the model: with a communicator registered, b2_backward itself launches the fused
+ * all-reduce + SGD of every gradient bucket on a side stream as soon as the bucket's last
+ * gradient has been produced (overlap with the rest of backward, reducer.hpp:524 semantics) and
+ * joins before returning to the caller's stream; optimizer.step() then has nothing left to
+ * launch.  momentum: fp32 [param_count].  enable=0 restores the plain backward. */
+int b2_model_set_ddp(b2_model *m, int enable, float *momentum_buf, float lr, float momentum, int algo,
+                     int64_t bucket_elems);
+/* step 0 clones the gradient into the momentum buffer (sgd.py): tell the model which step it is */
+int b2_model_ddp_first_step(b2_model *m, int first);
+int b2_model_num_buckets(const b2_model *m);
 
 /* ---- CUDA-graph capture of a step (launch-latency removal) ---------------- */
 int b2_graph_begin(void *stream);
