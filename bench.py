@@ -163,7 +163,8 @@ def run_b2(args):
 
     torch.manual_seed(0)
     net = b2.resnet18(num_classes=10, precision=args.precision).to(dev)
-    model = b2.DistributedDataParallel(net, device_ids=[dev]) if ns.distributed else net
+    model = (b2.DistributedDataParallel(net, device_ids=[dev], overlap=not args.no_overlap, bucket_cap_mb=args.bucket_mb)
+             if ns.distributed else net)
     criterion = b2.CrossEntropyLoss()
     optimizer = b2.SGD(model.parameters(), lr=0.001, momentum=0.9)
 
@@ -293,6 +294,8 @@ def main():
     ap.add_argument("--impl", default="b2", choices=["b2", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="DDP: one fused exchange at optimizer.step() instead of bucketed overlap")
+    ap.add_argument("--bucket-mb", type=float, default=32.0)
     ap.add_argument("--no-clocks", action="store_true", help="skip the nvidia-smi sampler (profiler runs)")
     args = ap.parse_args()
     if args.impl == "reference":

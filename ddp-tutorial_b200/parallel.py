@@ -106,7 +106,7 @@ class DistributedDataParallel:
     """
 
     def __init__(self, module, device_ids: Optional[List[int]] = None, algo: int = 0, overlap: bool = True,
-                 bucket_cap_mb: float = 8.0):
+                 bucket_cap_mb: float = 32.0):
         if not _state["distributed"]:
             raise B2Error("Default process group has not been initialized: call init_distributed(args) "
                           "under torchrun first (cifar_example_ddp.py:69)")
