@@ -66,6 +66,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 constexpr int kNumSMs = 148;
+// fused-BatchNorm sum buffers are replicated to spread same-address atomics: layout [copies][2][C]
+constexpr int kBnSumCopies = 8;
 
 // ---- conv geometry shared by every implementation ---------------------------
 struct ConvGeom {

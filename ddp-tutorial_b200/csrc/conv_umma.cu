@@ -220,8 +220,9 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
             for (int rr = 0; rr < 64; ++rr) { float x = sT[(r0 + rr) * 65 + c]; s0 += x; s1 = fmaf(x, x, s1); }
-            atomicAdd(p.stats + ch0 + c, s0);
-            atomicAdd(p.stats + p.out_C + ch0 + c, s1);
+            float *st = p.stats + (size_t)(blockIdx.x % kBnSumCopies) * 2 * p.out_C;
+            atomicAdd(st + ch0 + c, s0);
+            atomicAdd(st + p.out_C + ch0 + c, s1);
         }
         tc_fence_before();
     }

@@ -262,7 +262,7 @@ int Model::finalize() {
         if (o.type != OP_BN) continue;
         for (const Op &c : ops)
             if (c.type == OP_CONV && c.out == o.in && (c.use_umma || c.stem_umma)) o.bn_fused = true;
-        if (o.bn_fused) { sum_off[i] = sums_floats; sums_floats += 4 * (size_t)tensors[o.in].C; }
+        if (o.bn_fused) { sum_off[i] = sums_floats; sums_floats += 4 * (size_t)kBnSumCopies * tensors[o.in].C; }
     }
     size_t sums_off = reserve(sums_floats * 4 + 256);
     size_t wg_off = reserve(wg_floats * 4 + 256);
@@ -288,7 +288,7 @@ int Model::finalize() {
     bn_sums = (float *)(base + sums_off); bn_sums_bytes = sums_floats * 4;
     for (size_t i = 0; i < ops.size(); ++i)
         if (ops[i].type == OP_BN && ops[i].bn_fused) {
-            ops[i].fsum = bn_sums + sum_off[i]; ops[i].bsum = ops[i].fsum + 2 * (size_t)tensors[ops[i].in].C;
+            ops[i].fsum = bn_sums + sum_off[i]; ops[i].bsum = ops[i].fsum + 2 * (size_t)kBnSumCopies * tensors[ops[i].in].C;
         }
     if (precision == B2_PREC_BF16) { own_bf16 = (bf16 *)(base + bf_off); p_params_bf16 = own_bf16; }
     return 0;
@@ -352,6 +352,7 @@ int Model::set_ddp(bool enable, float *mom, float lr, float momentum, int algo, 
 Model::~Model() {
     drop_graphs();
     if (ddp_stream) { cudaStreamDestroy(ddp_stream); cudaEventDestroy(ddp_fork); cudaEventDestroy(ddp_join); }
+    if (wg_stream) { cudaStreamDestroy(wg_stream); cudaEventDestroy(wg_fork); cudaEventDestroy(wg_join); }
     if (cap_stream) cudaStreamDestroy(cap_stream);
     if (slab) cudaFree(slab);
 }
@@ -569,13 +570,31 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
     Tensor &tl = tensors[logits_tensor];
     B2_CUDA(cudaMemcpyAsync(tl.grad, dlogits, tl.numel * 4, cudaMemcpyDeviceToDevice, s));
     size_t next_bucket = 0;
-    bool forked = false;
+    bool forked = false, wg_used = false;
+    const bool async_wg = wgrad_async && !profiling;
+    if (async_wg && !wg_stream) {
+        B2_CUDA(cudaStreamCreateWithFlags(&wg_stream, cudaStreamNonBlocking));
+        B2_CUDA(cudaEventCreateWithFlags(&wg_fork, cudaEventDisableTiming));
+        B2_CUDA(cudaEventCreateWithFlags(&wg_join, cudaEventDisableTiming));
+    }
+    // stream for this op's weight-gradient kernels: forks from `s` at the call (dY is final there)
+    auto wgrad_stream = [&]() -> cudaStream_t {
+        if (!async_wg) return s;
+        cudaEventRecord(wg_fork, s);
+        cudaStreamWaitEvent(wg_stream, wg_fork, 0);
+        wg_used = true;
+        return wg_stream;
+    };
     auto flush_buckets = [&](int i) -> int {
         // every bucket whose last gradient was produced by ops[i]: exchange + apply on the side stream
         while (ddp_on && next_bucket < buckets.size() && buckets[next_bucket].after_op >= i) {
             const Bucket &bk = buckets[next_bucket++];
             B2_CUDA(cudaEventRecord(ddp_fork, s));
             B2_CUDA(cudaStreamWaitEvent(ddp_stream, ddp_fork, 0));
+            if (wg_used) {                                  // the bucket also needs the async weight gradients
+                B2_CUDA(cudaEventRecord(wg_join, wg_stream));
+                B2_CUDA(cudaStreamWaitEvent(ddp_stream, wg_join, 0));
+            }
             B2_TRY(comm_allreduce_sgd_range(ddp_mom, bk.off, bk.n, ddp_lr, ddp_momentum, ddp_first, ddp_algo,
                                             p_params_bf16, ddp_stream));
             forked = true;
@@ -591,8 +610,9 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
         case OP_CONV: {
             if (o.stem_umma) {
                 int ph = prof_begin(PC_CONV_WGRAD, 2.0 * o.g.M() * o.g.Co * o.g.K(), (double)o.vg.M() * o.kpad * 2 + to.numel * 2.0, s);
-                B2_TRY(umma_wgrad_launch(o.wplan, s));
-                B2_TRY(op_copy_2d_f32(o.dwpad, o.kpad, p_grads + o.w_off, o.g.K(), o.g.Co, o.g.K(), s));
+                cudaStream_t ws = wgrad_stream();
+                B2_TRY(umma_wgrad_launch(o.wplan, ws));
+                B2_TRY(op_copy_2d_f32(o.dwpad, o.kpad, p_grads + o.w_off, o.g.K(), o.g.Co, o.g.K(), ws));
                 prof_end(ph, s);
                 break;
             }
@@ -610,8 +630,11 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
             const double cflops = 2.0 * o.g.M() * o.g.Co * o.g.K();
             const double cbytes = ti.numel * (double)dt_size(ti.dt) + to.numel * (double)dt_size(to.dt);
             int ph = prof_begin(PC_CONV_WGRAD, o.use_umma ? o.wplan.flops : cflops, cbytes + (double)o.g.Co * o.g.K() * 4, s);
-            if (o.use_umma) B2_TRY(umma_wgrad_launch(o.wplan, s));
-            else B2_TRY(conv_simt_wgrad(o.g, ti.val, to.grad, ti.dt, p_grads + o.w_off, wgrad_ws, wgrad_floats, s));
+            {
+                cudaStream_t ws = wgrad_stream();
+                if (o.use_umma) B2_TRY(umma_wgrad_launch(o.wplan, ws));
+                else B2_TRY(conv_simt_wgrad(o.g, ti.val, to.grad, ti.dt, p_grads + o.w_off, wgrad_ws, wgrad_floats, ws));
+            }
             prof_end(ph, s);
             if (o.need_dgrad) {
                 const void *w = o.wdt == DT_BF16 ? (const void *)(p_params_bf16 + o.w_off) : (const void *)(p_params + o.w_off);
@@ -656,6 +679,10 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
             break;
         }
         B2_TRY(flush_buckets(i));
+    }
+    if (wg_used) {                                  // join the weight-gradient stream
+        B2_CUDA(cudaEventRecord(wg_join, wg_stream));
+        B2_CUDA(cudaStreamWaitEvent(s, wg_join, 0));
     }
     if (forked) {                                   // join: the caller's stream continues after the exchange
         B2_CUDA(cudaEventRecord(ddp_join, ddp_stream));

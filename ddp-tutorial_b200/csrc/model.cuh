@@ -84,6 +84,11 @@ struct Model {
     std::vector<Bucket> buckets;
     bool ddp_on = false;
     float *ddp_mom = nullptr; float ddp_lr = 0.f, ddp_momentum = 0.f; int ddp_algo = 0, ddp_first = 1;
+    // weight gradients are off the backward critical path (only the optimizer consumes them):
+    // they run on their own stream, forked after each layer's dY is final, joined at the end
+    cudaStream_t wg_stream = nullptr;
+    cudaEvent_t wg_fork = nullptr, wg_join = nullptr;
+    bool wgrad_async = true;
     cudaStream_t ddp_stream = nullptr;
     cudaEvent_t ddp_fork = nullptr, ddp_join = nullptr;
     int set_ddp(bool enable, float *mom, float lr, float momentum, int algo, int64_t bucket_elems);

@@ -727,8 +727,11 @@ k_bn_apply_fused(const T *__restrict__ x, T *__restrict__ y, const T *__restrict
     extern __shared__ float sm[];             // scale[C], shift[C]
     float *scale = sm, *shift = sm + C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        double mu = (double)fsum[c] / (double)M;
-        double var = (double)fsum[C + c] / (double)M - mu * mu;
+        float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kBnSumCopies; ++k) { t0 += fsum[(2 * k) * C + c]; t1 += fsum[(2 * k + 1) * C + c]; }
+        double mu = (double)t0 / (double)M;
+        double var = (double)t1 / (double)M - mu * mu;
         if (var < 0.0) var = 0.0;
         float is = (float)(1.0 / sqrt(var + (double)eps));
         float g = gamma[c];
@@ -811,10 +814,11 @@ k_bn_bwd_reduce_atomic(const T *__restrict__ x, const T *__restrict__ y, const T
         __syncthreads();
     }
     if (ty == 0) {
+        float *dst = bsum + (size_t)(blockIdx.y % kBnSumCopies) * 2 * C;     // spread same-address atomics over copies
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            atomicAdd(bsum + c0 + e, mine[e]);
-            atomicAdd(bsum + C + c0 + e, mine[8 + e]);
+            atomicAdd(dst + c0 + e, mine[e]);
+            atomicAdd(dst + C + c0 + e, mine[8 + e]);
         }
     }
 }
@@ -828,7 +832,9 @@ k_bn_bwd_apply_fused(const T *__restrict__ x, const T *__restrict__ y, const T *
     extern __shared__ float sm[];     // a[C], b[C], k[C]: dx = a*g + b*x + k   (per channel)
     float *ca = sm, *cb = sm + C, *ck = sm + 2 * C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float sg = bsum[c], sgx = bsum[C + c];
+        float sg = 0.f, sgx = 0.f;
+#pragma unroll
+        for (int k = 0; k < kBnSumCopies; ++k) { sg += bsum[(2 * k) * C + c]; sgx += bsum[(2 * k + 1) * C + c]; }
         float is = invstd[c], mu = mean[c], a = gamma[c] * is;
         float c1 = sg / (float)M, c2 = sgx / (float)M;
         // dx = a*(g - c1 - xhat*c2), xhat = (x - mu)*is
