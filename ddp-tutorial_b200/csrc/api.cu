@@ -1,6 +1,7 @@
 // extern "C" surface of libb2ddp.so -- see include/b2ddp.h for the contract and the
 // reference line each entry replaces.  Nothing throws across this boundary.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <new>
 #include <algorithm>
 
@@ -9,6 +10,7 @@
 namespace b2 {
 thread_local char g_err[1024] = {0};
 int64_t g_launches = 0;
+bool g_pdl = [] { const char *e = getenv("B2_PDL"); return !(e && e[0] == '0'); }();
 void set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

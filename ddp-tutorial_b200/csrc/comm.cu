@@ -113,6 +113,7 @@ template <int W, int MODE, bool ONESHOT>
 __global__ void __launch_bounds__(kCommThreads)
 k_allreduce(const CommPtrs P, int rank, float *__restrict__ mom_buf, int64_t off, int64_t n4 /* float4 count */,
             float scale, float lr, float momentum, int first, bf16 *__restrict__ mirror, uint32_t *epoch_mem, int *err) {
+    pdl_sync();
     peer_barrier<W>(P, rank, epoch_mem, 0, err);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,6 +185,7 @@ k_allreduce(const CommPtrs P, int rank, float *__restrict__ mom_buf, int64_t off
 template <int W>
 __global__ void __launch_bounds__(kCommThreads)
 k_barrier_only(const CommPtrs P, int rank, uint32_t *epoch_mem, int *err) {
+    pdl_sync();
     peer_barrier<W>(P, rank, epoch_mem, 0, err);
     peer_barrier<W>(P, rank, epoch_mem, 1, err);
 }

@@ -41,12 +41,36 @@ extern int64_t g_launches;
         if (_r != 0) return _r;                                                    \
     } while (0)
 
+// Programmatic dependent launch: every kernel is launched with the stream-serialization
+// attribute and begins with pdl_sync() (launch_dependents + wait), so the NEXT kernel's launch
+// latency and prologue overlap this kernel's execution while all of its global-memory traffic
+// still happens after this grid has completed and flushed.
+extern bool g_pdl;
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                        Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // every launch goes through this so b2_launch_count() is honest
 #define B2_LAUNCH(kernel, grid, block, smem, stream, ...)                          \
     do {                                                                           \
-        kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);  \
+        cudaError_t _le = b2::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream), __VA_ARGS__); \
         ++b2::g_launches;                                                          \
-        B2_CUDA(cudaGetLastError());                                               \
+        if (_le != cudaSuccess) {                                                  \
+            b2::set_error("%s:%d: launch of %s failed: %s", __FILE__, __LINE__, #kernel, cudaGetErrorString(_le)); \
+            return B2_ERR_CUDA;                                                    \
+        }                                                                          \
     } while (0)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -32,6 +32,7 @@ struct SimtArgs {
 template <int MODE, typename TA, typename TW, typename TC>
 __global__ void __launch_bounds__(256)
 k_conv_simt(const SimtArgs p) {
+    pdl_sync();
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
     const ConvGeom &g = p.g;
@@ -209,6 +210,7 @@ k_conv_simt(const SimtArgs p) {
 }
 
 __global__ void k_reduce_partials(const float *__restrict__ part, float *__restrict__ out, int64_t n, int splits) {
+    pdl_sync();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float s = 0.f;
         for (int z = 0; z < splits; ++z) s += part[(int64_t)z * n + i];

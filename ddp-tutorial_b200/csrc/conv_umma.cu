@@ -130,10 +130,12 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, 64); tmem_relinquish(); }
+    pdl_trigger();                 // the next kernel may begin its own prologue
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                    // everything below touches global memory of earlier kernels
 
     if (warp == 0) {
         if (lane == 0) {
@@ -264,10 +266,12 @@ k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUten
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -413,9 +417,7 @@ int umma_plan_dgrad(const ConvGeom &g, const bf16 *dy, const bf16 *w, bf16 *dx, 
 int umma_conv_launch(const UmmaConvPlan &plan, cudaStream_t s) {
     B2_CHECK(plan.valid, B2_ERR_STATE, "umma conv: plan not valid");
     std::call_once(g_attr_once, set_attrs);
-    k_tapgemm<<<plan.grid, 192, kTapSmem, s>>>(plan.a_map, plan.b_map, plan.p);
-    ++g_launches;
-    B2_CUDA(cudaGetLastError());
+    B2_LAUNCH(k_tapgemm, plan.grid, 192, kTapSmem, s, plan.a_map, plan.b_map, plan.p);
     return 0;
 }
 
@@ -476,6 +478,7 @@ int umma_plan_wgrad(const ConvGeom &g, const bf16 *x, const bf16 *dy, float *dw,
 
 // dW[co][tap_id*Ci + c] = sum_z partial[z][co][a*Ci + c]   (a = live-tap index), float4 lanes
 __global__ void k_wgrad_reduce(const float *__restrict__ part, float *__restrict__ dw, WgradParams p) {
+    pdl_sync();
     const int akc = p.out_pitch;                 // live taps * Ci
     const int64_t per_split = (int64_t)p.Co * akc;
     const int64_t n4 = per_split >> 2;
@@ -501,9 +504,7 @@ int umma_wgrad_launch(const UmmaWgradPlan &plan, cudaStream_t s) {
     B2_CHECK(plan.valid, B2_ERR_STATE, "umma wgrad: plan not valid");
     std::call_once(g_attr_once, set_attrs);
     const WgradParams &p = plan.p;
-    k_wgrad<<<plan.grid, 192, kWgSmem, s>>>(plan.x_map, plan.dy_map, plan.p);
-    ++g_launches;
-    B2_CUDA(cudaGetLastError());
+    B2_LAUNCH(k_wgrad, plan.grid, 192, kWgSmem, s, plan.x_map, plan.dy_map, plan.p);
     if (p.splits > 1) {
         int64_t n4 = (int64_t)p.Co * p.out_pitch / 4;
         int blocks = (int)ceil_div(n4, 256); if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;

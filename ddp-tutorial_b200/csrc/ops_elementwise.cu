@@ -26,6 +26,7 @@ static inline int grid_for(int64_t n, int block, int max_blocks = kNumSMs * 16) 
 // ---------------------------------------------------------------------------------
 template <typename T>
 __global__ void k_nchw_to_nhwc(const float *__restrict__ x, T *__restrict__ y, int N, int C, int H, int W) {
+    pdl_sync();
     int64_t total = (int64_t)N * C * H * W;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = i % C; int64_t r = i / C;
@@ -41,6 +42,7 @@ int op_nchw_to_nhwc(const float *x, void *y, int dt, int N, int C, int H, int W,
 }
 template <typename T>
 __global__ void k_nhwc_to_nchw(const T *__restrict__ x, float *__restrict__ y, int N, int C, int H, int W) {
+    pdl_sync();
     int64_t total = (int64_t)N * C * H * W;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int w = i % W; int64_t r = i / W;
@@ -55,6 +57,7 @@ int op_nhwc_to_nchw_f32(const void *x, int dt, float *y, int N, int C, int H, in
     return 0;
 }
 __global__ void k_f32_to_bf16(const float *__restrict__ x, bf16 *__restrict__ y, int64_t n) {
+    pdl_sync();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         y[i] = __float2bfloat16_rn(x[i]);
 }
@@ -63,6 +66,7 @@ int op_f32_to_bf16(const float *x, bf16 *y, int64_t n, cudaStream_t s) {
     return 0;
 }
 __global__ void k_f32_to_bf16_padded(const float *__restrict__ x, bf16 *__restrict__ y, int64_t rows, int k, int kpad) {
+    pdl_sync();
     int64_t total = rows * kpad;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i / kpad; int c = i - r * kpad;
@@ -92,6 +96,7 @@ __global__ void __launch_bounds__(256)
 k_bn_reduce(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy,
             const float *__restrict__ mean, const float *__restrict__ invstd, bool relu,
             int64_t M, int C, float *__restrict__ partial) {
+    pdl_sync();
     // FWD: partial = {sum x, sum x^2};  BWD: partial = {sum g, sum g*xhat}
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -135,6 +140,7 @@ __global__ void __launch_bounds__(128)
 k_bn_finalize_fwd(const float *__restrict__ partial, int nblk, int64_t M, int C, float eps,
                   float momentum, float *__restrict__ mean, float *__restrict__ invstd,
                   float *running_mean, float *running_var) {
+    pdl_sync();
     const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
     double s0 = 0.0, s1 = 0.0;
@@ -158,6 +164,7 @@ __global__ void __launch_bounds__(256)
 k_bn_apply(const T *__restrict__ x, T *__restrict__ y, const T *__restrict__ res,
            const float *__restrict__ mean, const float *__restrict__ invstd,
            const float *__restrict__ gamma, const float *__restrict__ beta, bool relu, int64_t total, int C) {
+    pdl_sync();
     for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * V; i < total; i += (int64_t)gridDim.x * blockDim.x * V) {
         int c0 = i % C;
         __align__(16) T xv[V], rv[V], ov[V];
@@ -199,6 +206,7 @@ __global__ void __launch_bounds__(128)
 k_bn_finalize_bwd(const float *__restrict__ partial, int nblk, int64_t M, int C,
                   const float *__restrict__ gamma, const float *__restrict__ invstd,
                   float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef) {
+    pdl_sync();
     const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
     double s0 = 0.0, s1 = 0.0;
@@ -217,6 +225,7 @@ __global__ void __launch_bounds__(256)
 k_bn_bwd_apply(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy, T *__restrict__ dx,
                T *__restrict__ dres, const float *__restrict__ mean, const float *__restrict__ invstd,
                const float *__restrict__ coef, bool relu, bool acc_dx, bool acc_dres, int64_t total, int C) {
+    pdl_sync();
     for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * V; i < total; i += (int64_t)gridDim.x * blockDim.x * V) {
         int c0 = i % C;
         __align__(16) T xv[V], yv[V], gv[V], ov[V], rv[V], pv[V];
@@ -270,6 +279,7 @@ int op_bn_backward(const void *x, const void *y, const void *dy, void *dx, void 
 template <typename T>
 __global__ void k_maxpool_fwd(const T *__restrict__ x, T *__restrict__ y, uint8_t *__restrict__ idx, int N, int Hi,
                               int Wi, int C, int k, int stride, int pad, int Ho, int Wo, bool out_nchw) {
+    pdl_sync();
     int64_t total = (int64_t)N * Ho * Wo * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = i % C; int64_t r = i / C;
@@ -301,6 +311,7 @@ int op_maxpool_forward(const void *x, void *y, uint8_t *idx, int dt, int N, int 
 template <typename T>
 __global__ void k_maxpool_bwd(const T *__restrict__ dy, const uint8_t *__restrict__ idx, T *__restrict__ dx, int N,
                               int Hi, int Wi, int C, int k, int stride, int pad, int Ho, int Wo, bool out_nchw, bool acc) {
+    pdl_sync();
     int64_t total = (int64_t)N * Hi * Wi * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = i % C; int64_t r = i / C;
@@ -335,6 +346,7 @@ int op_maxpool_backward(const void *dy, const uint8_t *idx, void *dx, int dt, in
 
 template <typename T>
 __global__ void k_avgpool_fwd(const T *__restrict__ x, float *__restrict__ y, int N, int HW, int C) {
+    pdl_sync();
     int64_t total = (int64_t)N * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = i % C; int64_t n = i / C;
@@ -349,6 +361,7 @@ int op_avgpool_forward(const void *x, int xdt, float *y, int N, int HW, int C, c
 }
 template <typename T>
 __global__ void k_avgpool_bwd(const float *__restrict__ dy, T *__restrict__ dx, int N, int HW, int C, bool acc) {
+    pdl_sync();
     int64_t total = (int64_t)N * HW * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = i % C; int64_t n = i / ((int64_t)HW * C);
@@ -367,6 +380,7 @@ int op_avgpool_backward(const float *dy, void *dx, int xdt, int N, int HW, int C
 // ---------------------------------------------------------------------------------
 template <typename T>
 __global__ void k_relu_mask(const T *__restrict__ y, T *__restrict__ dy, int64_t n) {
+    pdl_sync();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         if (!(to_f<T>(y[i]) > 0.f)) dy[i] = from_f<T>(0.f);
 }
@@ -377,6 +391,7 @@ int op_relu_mask(const void *y, void *dy, int dt, int64_t n, cudaStream_t s) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_bias_grad(const T *__restrict__ dy, int64_t M, int C, float *__restrict__ db) {
+    pdl_sync();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
     float s = 0.f;
@@ -403,6 +418,7 @@ int op_bias_grad(const void *dy, int dt, int64_t M, int C, float *db, cudaStream
 __global__ void __launch_bounds__(256)
 k_ce_loss_grad(const float *__restrict__ logits, const int64_t *__restrict__ labels, int B, int C,
                float *__restrict__ loss, float *__restrict__ dlogits) {
+    pdl_sync();
     float local = 0.f;
     const float invB = 1.f / (float)B;
     for (int r = threadIdx.x; r < B; r += blockDim.x) {
@@ -443,6 +459,7 @@ int op_ce_loss_grad(const float *logits, const int64_t *labels, int B, int C, fl
 __global__ void __launch_bounds__(256)
 k_sgd(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, int64_t n, float lr, float mom,
       float gscale, int first, bf16 *__restrict__ pb) {
+    pdl_sync();
     int64_t n4 = n >> 2;
     float4 *p4 = (float4 *)p; const float4 *g4 = (const float4 *)g; float4 *m4 = (float4 *)m;
     // torch semantics (sgd.py:_single_tensor_sgd): buf.mul_(momentum).add_(grad) is two
@@ -498,6 +515,7 @@ static inline int grid_for2(int64_t n, int block, int max_blocks = kNumSMs * 16)
 __global__ void __launch_bounds__(256)
 k_maxpool_fwd_bf16x8(const bf16 *__restrict__ x, bf16 *__restrict__ y, uint8_t *__restrict__ idx, int N, int Hi, int Wi,
                      int C, int k, int stride, int pad, int Ho, int Wo) {
+    pdl_sync();
     const int C8 = C >> 3;
     const int64_t total = (int64_t)N * Ho * Wo * C8;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -540,6 +558,7 @@ int op_maxpool_forward_bf16x8(const bf16 *x, bf16 *y, uint8_t *idx, int N, int H
 __global__ void __launch_bounds__(256)
 k_maxpool_bwd_bf16x8(const bf16 *__restrict__ dy, const uint8_t *__restrict__ idx, bf16 *__restrict__ dx, int N, int Hi,
                      int Wi, int C, int k, int stride, int pad, int Ho, int Wo, bool acc) {
+    pdl_sync();
     const int C8 = C >> 3;
     const int64_t total = (int64_t)N * Hi * Wi * C8;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -589,6 +608,7 @@ template <int KS, int CH>
 __global__ void __launch_bounds__(256)
 k_stem_im2col(const float *__restrict__ x, bf16 *__restrict__ col, int N, int H, int W, int stride, int pad,
               int Ho, int Wo, int kpad) {
+    pdl_sync();
     const int chunks = kpad >> 3;
     constexpr int K = KS * KS * CH;
     const int64_t total = (int64_t)N * Ho * Wo * chunks;
@@ -624,6 +644,7 @@ int op_stem_im2col(const float *x_nchw, bf16 *col, int N, int C, int H, int W, i
 }
 
 __global__ void k_copy_2d_f32(const float *__restrict__ src, int spitch, float *__restrict__ dst, int dpitch, int rows, int cols) {
+    pdl_sync();
     int64_t total = (int64_t)rows * cols;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = i % cols; int r = (int)(i / cols);
@@ -639,6 +660,7 @@ int op_copy_2d_f32(const float *src, int spitch, float *dst, int dpitch, int row
 __global__ void __launch_bounds__(256)
 k_fc_fwd(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias, float *__restrict__ y,
          int B, int K, int N, bool relu) {
+    pdl_sync();
     // one thread per output (b, n); K-loop with 4 independent accumulators
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * N) return;
@@ -667,6 +689,7 @@ int op_fc_forward(const float *x, const float *w, const float *bias, float *y, i
 __global__ void __launch_bounds__(256)
 k_fc_wgrad(const float *__restrict__ x, const float *__restrict__ dy, float *__restrict__ dw, float *__restrict__ db,
            int B, int K, int N) {
+    pdl_sync();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int kk = blockIdx.x * 32 + tx, n = blockIdx.y;
     float s = 0.f, sb = 0.f;
@@ -694,6 +717,7 @@ k_fc_wgrad(const float *__restrict__ x, const float *__restrict__ dy, float *__r
 }
 __global__ void __launch_bounds__(256)
 k_fc_dgrad(const float *__restrict__ w, const float *__restrict__ dy, float *__restrict__ dx, int B, int K, int N, bool acc) {
+    pdl_sync();
     const int64_t total = (int64_t)B * K;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int kk = i % K; int64_t b = i / K;
@@ -724,6 +748,7 @@ k_bn_apply_fused(const T *__restrict__ x, T *__restrict__ y, const T *__restrict
                  int64_t M, const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ save_mean,
                  float *__restrict__ save_invstd, float *running_mean, float *running_var, float eps, float momentum,
                  bool relu, int64_t total, int C) {
+    pdl_sync();
     extern __shared__ float sm[];             // scale[C], shift[C]
     float *scale = sm, *shift = sm + C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -779,6 +804,7 @@ __global__ void __launch_bounds__(256)
 k_bn_bwd_reduce_atomic(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy,
                        const float *__restrict__ mean, const float *__restrict__ invstd, bool relu, int64_t M, int C,
                        int opb /* channel octets per block: min(C/8, 32) */, float *__restrict__ bsum) {
+    pdl_sync();
     // each thread owns 8 consecutive channels (16-byte loads); 256/opb row lanes per block
     const int tx = threadIdx.x % opb, ty = threadIdx.x / opb, lanes = 256 / opb;
     const int c0 = (blockIdx.x * opb + tx) * 8;
@@ -829,6 +855,7 @@ k_bn_bwd_apply_fused(const T *__restrict__ x, const T *__restrict__ y, const T *
                      T *__restrict__ dres, const float *__restrict__ mean, const float *__restrict__ invstd,
                      const float *__restrict__ bsum, const float *__restrict__ gamma, float *__restrict__ dgamma,
                      float *__restrict__ dbeta, int64_t M, bool relu, bool acc_dx, bool acc_dres, int64_t total, int C) {
+    pdl_sync();
     extern __shared__ float sm[];     // a[C], b[C], k[C]: dx = a*g + b*x + k   (per channel)
     float *ca = sm, *cb = sm + C, *ck = sm + 2 * C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
