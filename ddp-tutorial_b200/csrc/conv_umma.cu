@@ -183,7 +183,10 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         uint32_t v[32];
-        float *sT = (float *)sA;                       // [128][65] fp32 staging for the BN statistics
+        float *sT = (float *)sA;                       // [128][65] fp32 staging for per-channel sums
+        float *sT2 = sT + 128 * 65;                    // second plane (spills into the B stages: 66.5 KB < 96 KB)
+        const bool want_fwd = p.stats != nullptr, want_bwd = p.bn_bsum != nullptr;
+        const int64_t pix_off = (((int64_t)n * p.out_H + h) * p.out_W + w) * p.out_C + ch0;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + half * 32, v);
@@ -205,24 +208,44 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
 #pragma unroll
                 for (int e = 0; e < 4; ++e) p2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
                 d4[j] = pk;
-                if (p.stats) {                         // statistics of the values BatchNorm will read (bf16-rounded)
+                const int col = half * 32 + j * 8;
+                if (want_fwd) {                        // statistics of the values BatchNorm will read (bf16-rounded)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         float2 rf = __bfloat1622float2(p2[e]);
-                        sT[r * 65 + half * 32 + j * 8 + 2 * e] = rf.x;
-                        sT[r * 65 + half * 32 + j * 8 + 2 * e + 1] = rf.y;
+                        sT[r * 65 + col + 2 * e] = rf.x;
+                        sT[r * 65 + col + 2 * e + 1] = rf.y;
+                    }
+                }
+                if (want_bwd) {                        // g = dY*[y>0],  g*xhat  of the BatchNorm that produced this tensor
+                    uint4 yr = *(const uint4 *)(p.bn_y + pix_off + col), xr = *(const uint4 *)(p.bn_x + pix_off + col);
+                    const __nv_bfloat162 *y2 = (const __nv_bfloat162 *)&yr, *x2 = (const __nv_bfloat162 *)&xr;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float2 g = __bfloat1622float2(p2[e]), yv = __bfloat1622float2(y2[e]), xv = __bfloat1622float2(x2[e]);
+                        const int c = ch0 + col + 2 * e;
+                        if (p.bn_relu) { if (!(yv.x > 0.f)) g.x = 0.f; if (!(yv.y > 0.f)) g.y = 0.f; }
+                        sT[r * 65 + col + 2 * e] = g.x;
+                        sT[r * 65 + col + 2 * e + 1] = g.y;
+                        sT2[r * 65 + col + 2 * e] = g.x * ((xv.x - __ldg(p.bn_mean + c)) * __ldg(p.bn_invstd + c));
+                        sT2[r * 65 + col + 2 * e + 1] = g.y * ((xv.y - __ldg(p.bn_mean + c + 1)) * __ldg(p.bn_invstd + c + 1));
                     }
                 }
             }
         }
-        if (p.stats) {
+        if (want_fwd || want_bwd) {
             asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
             const int e = (warp - 2) * 32 + lane;
             const int c = e & 63, r0 = (e >> 6) * 64;
             float s0 = 0.f, s1 = 0.f;
+            if (want_fwd) {
 #pragma unroll 8
-            for (int rr = 0; rr < 64; ++rr) { float x = sT[(r0 + rr) * 65 + c]; s0 += x; s1 = fmaf(x, x, s1); }
-            float *st = p.stats + (size_t)(blockIdx.x % kBnSumCopies) * 2 * p.out_C;
+                for (int rr = 0; rr < 64; ++rr) { float x = sT[(r0 + rr) * 65 + c]; s0 += x; s1 = fmaf(x, x, s1); }
+            } else {
+#pragma unroll 8
+                for (int rr = 0; rr < 64; ++rr) { s0 += sT[(r0 + rr) * 65 + c]; s1 += sT2[(r0 + rr) * 65 + c]; }
+            }
+            float *st = (want_fwd ? p.stats : p.bn_bsum) + (size_t)((blockIdx.x + blockIdx.z) % kBnSumCopies) * 2 * p.out_C;
             atomicAdd(st + ch0 + c, s0);
             atomicAdd(st + p.out_C + ch0 + c, s1);
         }

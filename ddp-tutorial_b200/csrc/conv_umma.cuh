@@ -28,7 +28,13 @@ struct TapGemmParams {
     int b_mn;                   // 0: B tile rows = output channel, cols = K (fprop)
                                 // 1: B tile rows = K (co), cols = output channel (dgrad reads the
                                 //    same [Co][taps*Ci] weight copy as an MN-major operand)
-    float *stats;               // optional [2][out_C] per-channel sum / sum of squares (atomics); may be null
+    float *stats;               // optional [copies][2][out_C] per-channel sum / sum of squares (atomics); may be null
+    // optional (dgrad that produces the FINAL gradient of a fused BatchNorm's output tensor): also
+    // accumulate that BatchNorm's backward sums  sum(g), sum(g*xhat),  g = dY * [y > 0]
+    float *bn_bsum;             // [copies][2][out_C]; null = off
+    const bf16 *bn_x, *bn_y;    // the BatchNorm's input / output (same NHWC shape as `out`)
+    const float *bn_mean, *bn_invstd;
+    int bn_relu;
 };
 
 struct UmmaConvPlan {

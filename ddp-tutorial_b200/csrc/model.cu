@@ -5,6 +5,7 @@
 // There is no autograd: the backward schedule is fixed when the model is built, every
 // gradient lands in the caller's flat fp32 grad vector (the DDP bucket, reducer.hpp:347).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include <string>
@@ -164,16 +165,20 @@ void Model::build_resnet(bool bottleneck, const int layers[4]) {
                 wd = add_conv_weight(pre + ".downsample.0.weight", planes * expansion, inplanes, 1, 1);
                 nd = add_bn_params(*this, pre + ".downsample.1", planes * expansion);
             }
-            int idn = t;
-            if (down) {
+            // main path first, the downsample branch after it: in backward the block's first conv is
+            // then the LAST writer of the block input's gradient (its dgrad epilogue can finalise
+            // the BatchNorm-backward sums of the tensor it completes)
+            int idn = t, o;
+            auto downsample = [&]() {
+                if (!down) return;
                 int d = op_conv(t, wd, -1, planes * expansion, 1, stride, 0, false, -1);
                 idn = op_bn(d, nd.g, nd.b, nd.rm, nd.rv, false, -1);
-            }
-            int o;
+            };
             if (!bottleneck) {
                 o = op_conv(t, w1, -1, planes, 3, stride, 1, false, -1);
                 o = op_bn(o, n1.g, n1.b, n1.rm, n1.rv, true, -1);
                 o = op_conv(o, w2, -1, planes, 3, 1, 1, false, -1);
+                downsample();
                 o = op_bn(o, n2.g, n2.b, n2.rm, n2.rv, true, idn);
             } else {
                 o = op_conv(t, w1, -1, planes, 1, 1, 0, false, -1);
@@ -181,6 +186,7 @@ void Model::build_resnet(bool bottleneck, const int layers[4]) {
                 o = op_conv(o, w2, -1, planes, 3, stride, 1, false, -1);
                 o = op_bn(o, n2.g, n2.b, n2.rm, n2.rv, true, -1);
                 o = op_conv(o, w3, -1, planes * 4, 1, 1, 0, false, -1);
+                downsample();
                 o = op_bn(o, n3.g, n3.b, n3.rm, n3.rv, true, idn);
             }
             t = o;
@@ -420,6 +426,24 @@ int Model::build_plans() {
         if (b.type != OP_BN || !b.bn_fused) continue;
         for (Op &c : ops)
             if (c.type == OP_CONV && c.out == b.in) c.fplan.p.stats = b.fsum;
+        // last writer of d(b.out) in backward order = its first consumer in forward order
+        b.bwd_sums_fused = false;
+        for (Op &c : ops) {
+            bool consumes = (c.in == b.out) || (c.res == b.out);
+            if (!consumes) continue;
+            bool covers_all = c.g.stride == 1 || c.g.kh >= c.g.stride;      // a 1x1 stride-2 dgrad only touches even pixels
+            // measured (r01): the fused epilogue's per-row x/y gathers cost more than the separate
+            // coalesced reduce pass saves (1.055 vs 1.010 ms/step) -> off until the epilogue is
+            // re-tiled for row-coalesced access (env B2_FUSE_BN_BWD=1 enables it for experiments)
+            static const bool enable = [] { const char *e = getenv("B2_FUSE_BN_BWD"); return e && e[0] == '1'; }();
+            if (enable && c.type == OP_CONV && c.use_umma && c.need_dgrad && c.in == b.out && covers_all) {
+                TapGemmParams &q = c.dplan.p;
+                q.bn_bsum = b.bsum; q.bn_x = (const bf16 *)tensors[b.in].val; q.bn_y = (const bf16 *)tensors[b.out].val;
+                q.bn_mean = b.bn.mean; q.bn_invstd = b.bn.invstd; q.bn_relu = b.relu ? 1 : 0;
+                b.bwd_sums_fused = true;
+            }
+            break;      // only the first consumer matters
+        }
     }
     plans_ready = true;
     return 0;
@@ -656,7 +680,7 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
             if (o.bn_fused)
                 B2_TRY(op_bn_backward_fused(ti.val, to.val, to.grad, ti.grad, o.res >= 0 ? tensors[o.res].grad : nullptr, ti.dt, M,
                                             ti.C, o.bsum, p_params + o.w_off, p_grads + o.w_off, p_grads + o.b_off, o.relu,
-                                            o.acc_in, o.acc_res, o.bn, s));
+                                            o.acc_in, o.acc_res, o.bwd_sums_fused, o.bn, s));
             else
             B2_TRY(op_bn_backward(ti.val, to.val, to.grad, ti.grad, o.res >= 0 ? tensors[o.res].grad : nullptr, ti.dt, M,
                                   ti.C, p_params + o.w_off, p_grads + o.w_off, p_grads + o.b_off, o.relu, o.acc_in,

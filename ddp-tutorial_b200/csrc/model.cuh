@@ -26,7 +26,8 @@ struct Op {
     bool need_dgrad, acc_in, acc_res;
     BnWork bn;
     bool bn_fused;               // statistics come from the producing conv's epilogue
-    float *fsum, *bsum;          // [2][C] each, inside the per-step zeroed arena
+    float *fsum, *bsum;          // [copies][2][C] each, inside the per-step zeroed arena
+    bool bwd_sums_fused;         // the dgrad that finalises this BN's output gradient also accumulates bsum
     uint8_t *idx;                // maxpool argmax
     int wdt, wpitch;             // conv: weight operand type / row pitch as the kernels see it
     bool use_umma;               // tcgen05 path (bf16, channel counts multiples of 64)

@@ -898,8 +898,9 @@ k_bn_bwd_apply_fused(const T *__restrict__ x, const T *__restrict__ y, const T *
 
 int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx, void *dres, int dt, int64_t M, int C,
                          float *bsum, const float *gamma, float *dgamma, float *dbeta, bool relu, bool acc_dx,
-                         bool acc_dres, const BnWork &w, cudaStream_t s) {
+                         bool acc_dres, bool sums_ready, const BnWork &w, cudaStream_t s) {
     B2_CHECK(dt == DT_BF16 && C % 8 == 0, B2_ERR_ARG, "bn fused: bf16 activations with C %% 8 == 0 only");
+    if (!sums_ready) {
     int opb = C / 8 < 32 ? C / 8 : 32;
     B2_CHECK((C / 8) % opb == 0 && 256 % opb == 0, B2_ERR_ARG, "bn fused: unsupported channel count %d", C);
     int gx = (C / 8) / opb;
@@ -909,6 +910,7 @@ int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx,
     dim3 grid(gx, (unsigned)want);
     B2_LAUNCH((k_bn_bwd_reduce_atomic<bf16>), grid, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, w.mean, w.invstd,
               relu, M, C, opb, bsum);
+    }
     int64_t total = M * C;
     int64_t blocks = ceil_div(total / 8, 256); if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
     B2_LAUNCH((k_bn_bwd_apply_fused<bf16, 8>), (int)blocks, 256, 3 * C * sizeof(float), s, (const bf16 *)x, (const bf16 *)y,
