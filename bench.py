@@ -162,7 +162,7 @@ def run_b2(args):
     torch.cuda.set_device(dev)
 
     torch.manual_seed(0)
-    net = b2.resnet18(num_classes=10, precision=args.precision).to(dev)
+    net = getattr(b2, MODEL)(num_classes=10, precision=args.precision).to(dev)
     model = (b2.DistributedDataParallel(net, device_ids=[dev], overlap=not args.no_overlap, bucket_cap_mb=args.bucket_mb)
              if ns.distributed else net)
     criterion = b2.CrossEntropyLoss()
@@ -268,8 +268,8 @@ def run_b2(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": f"resnet18(num_classes=10) training step, per-GPU batch {BATCH}, 3x32x32 synthetic "
-                                   f"(BASELINE configs[{1 if n == 1 else 2}])",
+            "config": {"workload": f"{MODEL}(num_classes=10) training step, per-GPU batch {BATCH}, 3x32x32 synthetic "
+                                   f"(BASELINE configs[{(1 if n == 1 else 2) if MODEL == 'resnet18' else 3}])",
                        "global_batch": n * BATCH, "parallelism": f"dp{n}",
                        "precision": "bf16 activations+weight copies, fp32 accumulate, fp32 master+momentum"
                        if args.precision == "bf16" else "fp32",
@@ -287,17 +287,25 @@ def run_b2(args):
 
 
 def main():
+    global MODEL, BATCH, METRIC
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b2", choices=["b2", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--model", default="resnet18", choices=["resnet18", "resnet50"],
+                    help="resnet18 = the headline config; resnet50 (per-GPU batch 256) = BASELINE configs[3]")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 512 for resnet18, 256 for resnet50)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="DDP: one fused exchange at optimizer.step() instead of bucketed overlap")
     ap.add_argument("--bucket-mb", type=float, default=32.0)
     ap.add_argument("--no-clocks", action="store_true", help="skip the nvidia-smi sampler (profiler runs)")
     args = ap.parse_args()
+    MODEL = args.model
+    BATCH = args.batch or (512 if MODEL == "resnet18" else 256)
+    if MODEL != "resnet18":
+        METRIC = METRIC.replace("ResNet-18", "ResNet-50")
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -231,3 +231,61 @@ def test_resnet18_bf16_step0_within_bf16_noise():
     assert abs(losses[0] - r64["loss"][0]) < max(2 * abs(ac_loss - r64["loss"][0]), 5e-3)
     assert cos(mine, truth) > cos(ac, truth) - 0.02, (cos(mine, truth), cos(ac, truth))
     assert cos(mine, truth) > 0.9
+
+
+def test_resnet50_bf16_runs_and_tracks_oracle():
+    """BASELINE configs[3] model on the tcgen05 path: step-0 loss near the fp32 oracle, loss falls."""
+    r = O.train("resnet50", seed=0, batch=64, steps=1)
+    torch.manual_seed(0)
+    net = b2.resnet50(num_classes=10, precision="bf16").to(DEV)
+    losses, _ = run_b2(net, r["x"], r["y"], 8)
+    assert abs(losses[0] - r["loss"][0]) < 5e-2, (losses[0], r["loss"][0])
+    assert losses[-1] < losses[0]
+    assert all(np.isfinite(losses))
+
+
+def test_graph_replay_equals_eager():
+    """CUDA-graph replay (incl. the forked weight-gradient stream and PDL edges) must reproduce the
+    eager launches: same loss curve for ResNet-18 fp32 (deterministic kernels) with graphs on / off."""
+    gen = O.data_generator(0)
+    x, y = O.synthetic_batch(gen, 32)
+    curves = []
+    for graphs in (True, False):
+        torch.manual_seed(0)
+        net = b2.resnet18(num_classes=10, precision="fp32").to(DEV)
+        net.engine.set_graphs(graphs)
+        losses, _ = run_b2(net, x, y, 8)
+        curves.append(losses)
+    assert curves[0] == curves[1], curves
+
+
+def test_persistent_logits_and_batch_size_switch():
+    """One engine serves several batch sizes (one static graph each) over the same parameters."""
+    torch.manual_seed(0)
+    net = b2.Net().to(DEV)
+    crit = b2.CrossEntropyLoss()
+    opt = b2.SGD(net.parameters(), lr=0.001, momentum=0.9)
+    gen = O.data_generator(3)
+    for B in (4, 16, 4, 7):
+        x, y = O.synthetic_batch(gen, B)
+        out = net(x.to(DEV))
+        assert tuple(out.shape) == (B, 10)
+        loss = crit(out, y.to(DEV)); loss.backward(); opt.step()
+        assert np.isfinite(loss.item())
+
+
+def test_error_paths_on_gpu():
+    net = b2.Net().to(DEV)
+    with pytest.raises(b2.B2Error):
+        net(torch.zeros(4, 3, 32, 32))                       # CPU tensor into a CUDA model
+    with pytest.raises(b2.B2Error):
+        net(torch.zeros(4, 3, 16, 16, device=DEV))           # wrong spatial size
+    with pytest.raises(b2.B2Error):
+        net(torch.zeros(0, 3, 32, 32, device=DEV))           # empty batch
+    out = net(torch.zeros(4, 3, 32, 32, device=DEV))
+    with pytest.raises(b2.B2Error):
+        b2.CrossEntropyLoss()(out, torch.zeros(3, dtype=torch.long, device=DEV))    # ragged labels
+    loss = b2.CrossEntropyLoss()(out, torch.zeros(4, dtype=torch.long, device=DEV))
+    loss.backward()
+    with pytest.raises(b2.B2Error):
+        loss.backward()                                      # static graph: no double backward
