@@ -239,7 +239,7 @@ int Model::finalize() {
             wg_floats = std::max(wg_floats, conv_simt_wgrad_workspace(o.g));
             o.wdt = DT_F32; o.wpitch = o.g.K();
             o.is_fc = tensors[o.in].dt == DT_F32 && tensors[o.out].dt == DT_F32 && o.g.kh == 1 && o.g.Hi == 1 && o.g.Wi == 1 &&
-                      o.g.stride == 1 && o.g.pad == 0 && o.g.Co <= 32 && kind != B2_MODEL_NET;
+                      o.g.stride == 1 && o.g.pad == 0 && o.g.Co <= 16 && kind != B2_MODEL_NET;
             if (tensors[o.in].dt == DT_BF16 && o.in == input_tensor && conv_impl == 1 && !o.relu && o.b_off < 0 && o.g.Co % 64 == 0) {
                 o.kpad = (o.g.K() + 63) / 64 * 64;
                 ConvGeom v{};

@@ -602,22 +602,32 @@ int op_maxpool_backward_bf16x8(const bf16 *dy, const uint8_t *idx, bf16 *dx, int
     return 0;
 }
 
-// ---- stem im2col: one thread per (output pixel, 8 consecutive columns) -> one 16-byte store.
-// KS / CH are compile-time so the (kh, kw, c) decode is multiply-shift, not integer division.
+// ---- stem im2col.  One block per (image, output row): the KS input rows x CH channels the row
+// needs are staged in shared memory with coalesced loads, then every thread emits 16-byte
+// chunks of the bf16 im2col rows (column order (kh, kw, c), zero beyond KS*KS*CH).
 template <int KS, int CH>
 __global__ void __launch_bounds__(256)
 k_stem_im2col(const float *__restrict__ x, bf16 *__restrict__ col, int N, int H, int W, int stride, int pad,
               int Ho, int Wo, int kpad) {
     pdl_sync();
-    const int chunks = kpad >> 3;
+    extern __shared__ float srow[];                 // [KS][CH][W + 2*pad]  (zero padded left/right)
+    const int Wp = W + 2 * pad;
+    const int n = blockIdx.x / Ho, ho = blockIdx.x - n * Ho;
+    const float *xn = x + (int64_t)n * CH * H * W;
+    for (int i = threadIdx.x; i < KS * CH * Wp; i += blockDim.x) {
+        const int wp = i % Wp; const int t = i / Wp;
+        const int c = t % CH, kh = t / CH;
+        const int hi = ho * stride - pad + kh, wi = wp - pad;
+        float v = 0.f;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = xn[((int64_t)c * H + hi) * W + wi];
+        srow[i] = v;
+    }
+    __syncthreads();
     constexpr int K = KS * KS * CH;
-    const int64_t total = (int64_t)N * Ho * Wo * chunks;
-    const int HoWo = Ho * Wo;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int ch = (int)(i % chunks); const int m = (int)(i / chunks);
-        const int n = m / HoWo; const int rem = m - n * HoWo;
-        const int ho = rem / Wo, wo = rem - ho * Wo;
-        const float *xn = x + (int64_t)n * CH * H * W;
+    const int chunks = kpad >> 3;
+    bf16 *orow = col + ((int64_t)n * Ho + ho) * Wo * kpad;
+    for (int i = threadIdx.x; i < Wo * chunks; i += blockDim.x) {
+        const int ch = i % chunks, wo = i / chunks;
         __align__(16) bf16 o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -626,20 +636,19 @@ k_stem_im2col(const float *__restrict__ x, bf16 *__restrict__ col, int N, int H,
             if (kk < K) {
                 const int tap = kk / CH, c = kk - tap * CH;
                 const int kh = tap / KS, kw = tap - kh * KS;
-                const int hi = ho * stride - pad + kh, wi = wo * stride - pad + kw;
-                if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = __ldg(xn + ((int64_t)c * H + hi) * W + wi);
+                v = srow[(kh * CH + c) * Wp + wo * stride + kw];
             }
             o[e] = __float2bfloat16_rn(v);
         }
-        *(uint4 *)(col + (int64_t)m * kpad + ch * 8) = *(uint4 *)o;
+        *(uint4 *)(orow + (int64_t)wo * kpad + ch * 8) = *(uint4 *)o;
     }
 }
 int op_stem_im2col(const float *x_nchw, bf16 *col, int N, int C, int H, int W, int k, int stride, int pad, int Ho, int Wo,
                    int kpad, cudaStream_t s) {
     B2_CHECK(kpad % 8 == 0 && kpad >= k * k * C, B2_ERR_ARG, "stem im2col: bad kpad %d", kpad);
     B2_CHECK(k == 7 && C == 3, B2_ERR_UNSUPPORTED, "stem im2col: only the 7x7 / 3-channel ResNet stem is instantiated");
-    int64_t total = (int64_t)N * Ho * Wo * (kpad / 8);
-    B2_LAUNCH((k_stem_im2col<7, 3>), grid_for2(total, 256), 256, 0, s, x_nchw, col, N, H, W, stride, pad, Ho, Wo, kpad);
+    size_t smem = (size_t)k * C * (W + 2 * pad) * sizeof(float);
+    B2_LAUNCH((k_stem_im2col<7, 3>), N * Ho, 256, smem, s, x_nchw, col, N, H, W, stride, pad, Ho, Wo, kpad);
     return 0;
 }
 
@@ -657,32 +666,50 @@ int op_copy_2d_f32(const float *src, int spitch, float *dst, int dpitch, int row
 }
 
 // ---- classifier head, fp32.  forward: one warp per sample; N <= 32 outputs
+// one warp per sample; the weight matrix is staged in shared memory in K-chunks of 512 (every
+// block reading the same 20 KB straight from L2 serialises on the hot lines: 32 us -> ~4 us)
+template <int NMAX>
 __global__ void __launch_bounds__(256)
 k_fc_fwd(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias, float *__restrict__ y,
          int B, int K, int N, bool relu) {
     pdl_sync();
-    // one thread per output (b, n); K-loop with 4 independent accumulators
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= (int64_t)B * N) return;
-    const int n = (int)(i % N); const int64_t b = i / N;
-    const float *xr = x + b * K, *wr = w + (int64_t)n * K;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int kk = 0;
-    if ((K & 3) == 0) {
-        for (; kk < K; kk += 4) {
-            float4 xv = *(const float4 *)(xr + kk), wv = *(const float4 *)(wr + kk);
-            a0 = fmaf(xv.x, wv.x, a0); a1 = fmaf(xv.y, wv.y, a1); a2 = fmaf(xv.z, wv.z, a2); a3 = fmaf(xv.w, wv.w, a3);
-        }
-    } else {
-        for (; kk < K; ++kk) a0 = fmaf(xr[kk], wr[kk], a0);
+    constexpr int KC = 512;
+    __shared__ float sw[NMAX * KC];
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const bool active = warp < B;
+    const float *xr = x + (int64_t)(active ? warp : 0) * K;
+    float acc[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += KC) {
+        const int kc = K - k0 < KC ? K - k0 : KC;
+        __syncthreads();
+        for (int i = threadIdx.x; i < N * kc; i += blockDim.x) { int n = i / kc, kk = i - n * kc; sw[n * KC + kk] = w[(int64_t)n * K + k0 + kk]; }
+        __syncthreads();
+        if (active)
+            for (int kk = lane; kk < kc; kk += 32) {
+                const float xv = xr[k0 + kk];
+#pragma unroll
+                for (int n = 0; n < NMAX; ++n)
+                    if (n < N) acc[n] = fmaf(xv, sw[n * KC + kk], acc[n]);
+            }
     }
-    float s = (a0 + a1) + (a2 + a3);
-    if (bias) s += bias[n];
-    if (relu) s = s > 0.f ? s : 0.f;
-    y[i] = s;
+    if (!active) return;
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) {
+        if (n < N) {
+            float s = warp_sum(acc[n]);
+            if (lane == 0) {
+                if (bias) s += bias[n];
+                if (relu) s = s > 0.f ? s : 0.f;
+                y[(int64_t)warp * N + n] = s;
+            }
+        }
+    }
 }
 int op_fc_forward(const float *x, const float *w, const float *bias, float *y, int B, int K, int N, bool relu, cudaStream_t s) {
-    B2_LAUNCH(k_fc_fwd, (int)ceil_div((int64_t)B * N, 128), 128, 0, s, x, w, bias, y, B, K, N, relu);
+    B2_CHECK(N <= 16, B2_ERR_UNSUPPORTED, "fc head: at most 16 outputs");
+    B2_LAUNCH((k_fc_fwd<16>), (int)ceil_div((int64_t)B * 32, 256), 256, 0, s, x, w, bias, y, B, K, N, relu);
     return 0;
 }
 // dW[n][k] = sum_b dy[b][n] x[b][k]: block = 32 k-columns x 8 batch lanes, fixed-order smem combine
@@ -793,7 +820,7 @@ int op_bn_forward_fused(const void *x, void *y, const void *res, int dt, int64_t
                         float momentum, bool relu, const BnWork &w, cudaStream_t s) {
     B2_CHECK(dt == DT_BF16 && C % 8 == 0, B2_ERR_ARG, "bn fused: bf16 activations with C %% 8 == 0 only");
     int64_t total = M * C;
-    int64_t blocks = ceil_div(total / 8, 256); if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    int64_t blocks = ceil_div(total / 8, 256); if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
     B2_LAUNCH((k_bn_apply_fused<bf16, 8>), (int)blocks, 256, 2 * C * sizeof(float), s, (const bf16 *)x, (bf16 *)y, (const bf16 *)res,
               fsum, M, gamma, beta, w.mean, w.invstd, running_mean, running_var, eps, momentum, relu, total, C);
     return 0;
@@ -896,10 +923,84 @@ k_bn_bwd_apply_fused(const T *__restrict__ x, const T *__restrict__ y, const T *
     }
 }
 
+// Small feature maps (M rows <= 4096): ONE kernel, one block per 8-channel octet: reduce the
+// sums over all rows, derive the coefficients, apply (second read comes from L2).  No atomics.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_bn_bwd_small(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy, T *__restrict__ dx,
+               T *__restrict__ dres, const float *__restrict__ mean, const float *__restrict__ invstd,
+               const float *__restrict__ gamma, float *__restrict__ dgamma, float *__restrict__ dbeta, int64_t M, int C,
+               bool relu, bool acc_dx, bool acc_dres) {
+    pdl_sync();
+    const int c0 = blockIdx.x * 8;
+    float s0[8], s1[8], mu[8], is[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s0[e] = 0.f; s1[e] = 0.f; mu[e] = mean[c0 + e]; is[e] = invstd[c0 + e]; }
+    for (int64_t r = threadIdx.x; r < M; r += blockDim.x) {
+        __align__(16) T xv[8], yv[8], gv[8];
+        *(uint4 *)xv = *(const uint4 *)(x + r * C + c0);
+        *(uint4 *)gv = *(const uint4 *)(dy + r * C + c0);
+        if (relu) *(uint4 *)yv = *(const uint4 *)(y + r * C + c0);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float g = to_f<T>(gv[e]);
+            if (relu && !(to_f<T>(yv[e]) > 0.f)) g = 0.f;
+            s0[e] += g; s1[e] += g * ((to_f<T>(xv[e]) - mu[e]) * is[e]);
+        }
+    }
+    __shared__ float red[8][16];
+    __shared__ float tot[16];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s0[e] = warp_sum(s0[e]); s1[e] = warp_sum(s1[e]); }
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { red[wid][e] = s0[e]; red[wid][8 + e] = s1[e]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        float t = 0.f;
+        for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+        tot[threadIdx.x] = t;
+        if (threadIdx.x < 8) dbeta[c0 + threadIdx.x] = t; else dgamma[c0 + threadIdx.x - 8] = t;
+    }
+    __syncthreads();
+    float ca[8], cb[8], ck[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        float a = gamma[c0 + e] * is[e], c1 = tot[e] / (float)M, c2 = tot[8 + e] / (float)M;
+        ca[e] = a; cb[e] = -a * c2 * is[e]; ck[e] = -a * c1 + a * c2 * is[e] * mu[e];
+    }
+    for (int64_t r = threadIdx.x; r < M; r += blockDim.x) {
+        __align__(16) T xv[8], yv[8], gv[8], ov[8], rv[8], pv[8];
+        *(uint4 *)xv = *(const uint4 *)(x + r * C + c0);
+        *(uint4 *)gv = *(const uint4 *)(dy + r * C + c0);
+        if (relu) *(uint4 *)yv = *(const uint4 *)(y + r * C + c0);
+        if (acc_dx) *(uint4 *)pv = *(const uint4 *)(dx + r * C + c0);
+        if (dres && acc_dres) *(uint4 *)rv = *(const uint4 *)(dres + r * C + c0);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float g = to_f<T>(gv[e]);
+            if (relu && !(to_f<T>(yv[e]) > 0.f)) g = 0.f;
+            float d = fmaf(ca[e], g, fmaf(cb[e], to_f<T>(xv[e]), ck[e]));
+            if (acc_dx) d += to_f<T>(pv[e]);
+            ov[e] = from_f<T>(d);
+            if (dres) { float rr = g; if (acc_dres) rr += to_f<T>(rv[e]); rv[e] = from_f<T>(rr); }
+        }
+        *(uint4 *)(dx + r * C + c0) = *(uint4 *)ov;
+        if (dres) *(uint4 *)(dres + r * C + c0) = *(uint4 *)rv;
+    }
+}
+
 int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx, void *dres, int dt, int64_t M, int C,
                          float *bsum, const float *gamma, float *dgamma, float *dbeta, bool relu, bool acc_dx,
                          bool acc_dres, bool sums_ready, const BnWork &w, cudaStream_t s) {
     B2_CHECK(dt == DT_BF16 && C % 8 == 0, B2_ERR_ARG, "bn fused: bf16 activations with C %% 8 == 0 only");
+    if (!sums_ready && M <= 1024 && C >= 512) {      // measured: wins only for the 1x1-spatial stage
+        B2_LAUNCH((k_bn_bwd_small<bf16>), C / 8, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, (bf16 *)dx,
+                  (bf16 *)dres, w.mean, w.invstd, gamma, dgamma, dbeta, M, C, relu, acc_dx, acc_dres);
+        return 0;
+    }
     if (!sums_ready) {
     int opb = C / 8 < 32 ? C / 8 : 32;
     B2_CHECK((C / 8) % opb == 0 && 256 % opb == 0, B2_ERR_ARG, "bn fused: unsupported channel count %d", C);
@@ -912,7 +1013,7 @@ int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx,
               relu, M, C, opb, bsum);
     }
     int64_t total = M * C;
-    int64_t blocks = ceil_div(total / 8, 256); if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    int64_t blocks = ceil_div(total / 8, 256); if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
     B2_LAUNCH((k_bn_bwd_apply_fused<bf16, 8>), (int)blocks, 256, 3 * C * sizeof(float), s, (const bf16 *)x, (const bf16 *)y,
               (const bf16 *)dy, (bf16 *)dx, (bf16 *)dres, w.mean, w.invstd, bsum, gamma, dgamma, dbeta, M, relu, acc_dx, acc_dres,
               total, C);
