@@ -65,7 +65,9 @@ __device__ __forceinline__ void st_peer_f4(float *p, float4 v) {
 
 // All W ranks launch the same grid; block b of every rank meets block b of every other rank.
 // phase selects one of two flag banks so that back-to-back barriers never alias.
-template <int W>
+// FENCE: publish this CTA's earlier (peer) stores system-wide before signalling; not needed when
+// the barrier only says "I have arrived / I am done reading".
+template <int W, bool FENCE = true>
 __device__ __forceinline__ void peer_barrier(const CommPtrs &P, int rank, uint32_t *epoch_mem, int phase, int *err) {
     __syncthreads();
     __shared__ uint32_t s_epoch;
@@ -74,7 +76,7 @@ __device__ __forceinline__ void peer_barrier(const CommPtrs &P, int rank, uint32
         epoch_mem[phase * kCommBlocks + blockIdx.x] = e;
         s_epoch = e;
     }
-    __threadfence_system();      // publish this thread's earlier stores (incl. to peers)
+    if (FENCE) __threadfence_system();      // publish this thread's earlier stores (incl. to peers)
     __syncthreads();
     const uint32_t e = s_epoch;
     if (threadIdx.x < W) {
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(kCommThreads)
 k_allreduce(const CommPtrs P, int rank, float *__restrict__ mom_buf, int64_t off, int64_t n4 /* float4 count */,
             float scale, float lr, float momentum, int first, bf16 *__restrict__ mirror, uint32_t *epoch_mem, int *err) {
     pdl_sync();
-    peer_barrier<W>(P, rank, epoch_mem, 0, err);
+    peer_barrier<W, false>(P, rank, epoch_mem, 0, err);      // earlier kernels' stores are already visible
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ONESHOT) {
@@ -131,7 +133,7 @@ k_allreduce(const CommPtrs P, int rank, float *__restrict__ mom_buf, int64_t off
                 *(float4 *)(P.params[rank] + e) = p;
                 if (mirror) st_bf16x4(mirror + e, p);
             }
-            peer_barrier<W>(P, rank, epoch_mem, 1, err);      // peers are done reading my grads
+            peer_barrier<W, false>(P, rank, epoch_mem, 1, err);      // peers are done reading my grads
         } else {
             // at most one float4 per thread (host guarantees n4 <= grid*block): read all, barrier, write own
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -142,7 +144,7 @@ k_allreduce(const CommPtrs P, int rank, float *__restrict__ mom_buf, int64_t off
                 for (int r = 1; r < W; ++r) acc = f4_add(acc, ld_peer_f4(P.grads[r] + e));
                 acc = f4_scale(acc, scale);
             }
-            peer_barrier<W>(P, rank, epoch_mem, 1, err);
+            peer_barrier<W, false>(P, rank, epoch_mem, 1, err);
             if (tid < n4) *(float4 *)(P.grads[rank] + e) = acc;
         }
     } else {
@@ -205,11 +207,14 @@ static int launch_allreduce(int64_t off, int64_t n, float *m, float scale, float
     bool oneshot;
     if (algo == 1) oneshot = true;
     else if (algo == 2) oneshot = false;
-    else oneshot = (n * 4 <= 512 * 1024);
+    else oneshot = (n * 4 * (int64_t)c.world <= ((int64_t)8 << 20));   // bytes each rank reads in one-shot mode
     if (MODE == 0 && oneshot && n4 > cap) oneshot = false;
     if (c.world == 1) oneshot = true;
+    // small messages: only as many blocks as there is data (same on every rank: a function of n)
+    int blocks = kCommBlocks;
+    if (oneshot) { int64_t need = (n4 + kCommThreads - 1) / kCommThreads; if (need < blocks) blocks = need < 1 ? 1 : (int)need; }
 #define LAUNCH_W(Wv)                                                                                              \
-    if (oneshot) { B2_LAUNCH((k_allreduce<Wv, MODE, true>), kCommBlocks, kCommThreads, 0, s, c.ptrs, c.rank, m, off, n4, \
+    if (oneshot) { B2_LAUNCH((k_allreduce<Wv, MODE, true>), blocks, kCommThreads, 0, s, c.ptrs, c.rank, m, off, n4, \
                              scale, lr, momentum, first, mirror, c.epoch, c.err); }                                   \
     else { B2_LAUNCH((k_allreduce<Wv, MODE, false>), kCommBlocks, kCommThreads, 0, s, c.ptrs, c.rank, m, off, n4, scale,   \
                      lr, momentum, first, mirror, c.epoch, c.err); }
