@@ -44,6 +44,8 @@ _SIGS = {
     "b2_model_profile_collect": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i)]),
     "b2_model_num_ops": (_i, [_vp]),
     "b2_model_read_activation": (_i, [_vp, _i, _i, _vp, _i64, C.POINTER(_i64), C.POINTER(_i), _vp]),
+    "b2_preprocess_u8": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp]),
+    "b2_argmax_count": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "b2_conv_test": (_i, [_i] * 11 + [_vp, _vp, _vp, _vp, _vp]),
     "b2_ce_loss_grad": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "b2_sgd": (_i, [_vp, _vp, _vp, _i64, _f, _f, _f, _i, _vp, _vp]),

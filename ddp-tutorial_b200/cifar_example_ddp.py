@@ -7,8 +7,9 @@ from ``torchrun --nproc_per_node=N``), same construction order and step body
 
     torchrun --nproc_per_node=8 ddp-tutorial_b200/cifar_example_ddp.py --model resnet18 --batch-size 512
 
-Input is synthetic CIFAR-10-shaped data (3x32x32, N(0,1); uniform labels): the dataset download
-and DataLoader of the reference are outside the hot path this build covers.
+With ``./data/cifar-10-batches-py`` present the uint8 images live in HBM, are indexed with the
+reference's ``DistributedSampler`` semantics and normalised on the device (SURVEY.md 8f rows 1, 3);
+otherwise (no network here, so no download) the input is synthetic CIFAR-10-shaped data.
 """
 import argparse
 import os
@@ -18,6 +19,24 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ddp_tutorial_b200 as b2  # noqa: E402
+
+
+def load_cifar10(root, train):
+    """CIFAR-10 python batches as uint8 [N,32,32,3] + int64 labels (what torchvision.datasets.CIFAR10
+    decodes, cifar_example_ddp.py:67-68); None when the files are not there (no network in this build)."""
+    import pickle
+    import numpy as np
+    base = os.path.join(root, "cifar-10-batches-py")
+    names = [f"data_batch_{i}" for i in range(1, 6)] if train else ["test_batch"]
+    if not all(os.path.exists(os.path.join(base, n)) for n in names):
+        return None
+    xs, ys = [], []
+    for n in names:
+        with open(os.path.join(base, n), "rb") as f:
+            d = pickle.load(f, encoding="latin1")
+        xs.append(np.asarray(d["data"], dtype=np.uint8).reshape(-1, 3, 32, 32).transpose(0, 2, 3, 1))
+        ys.extend(d["labels"])
+    return torch.from_numpy(np.ascontiguousarray(np.concatenate(xs))), torch.tensor(ys, dtype=torch.int64)
 
 
 def main(args):
@@ -35,13 +54,24 @@ def main(args):
     optimizer = b2.SGD(net.parameters(), lr=0.001, momentum=0.9)              # :86
 
     gen = torch.Generator().manual_seed(args.seed + 1 + rank)
+    train = load_cifar10(args.data, True)
+    test = load_cifar10(args.data, False)
+    world = args.world_size if args.distributed else 1
+    if train is not None:                                                     # :67-71, images resident in HBM
+        sampler_train = b2.DistributedSampler(train[0].shape[0], num_replicas=world, rank=rank, shuffle=True)
+        trainloader = b2.DeviceCifarLoader(train[0], train[1], batch_size, sampler_train, args.gpu)
+
+    def synthetic():
+        for _ in range(args.steps):
+            x = torch.randn(batch_size, 3, 32, 32, generator=gen).pin_memory()
+            y = torch.randint(0, 10, (batch_size,), generator=gen).pin_memory()
+            yield x.to(args.gpu, non_blocking=True), y.to(args.gpu, non_blocking=True)          # :97-98
+
     for epoch in range(args.epochs):                                          # :90
         running_loss = 0.0
-        for i in range(args.steps):                                           # :94
-            inputs = torch.randn(batch_size, 3, 32, 32, generator=gen).pin_memory()
-            labels = torch.randint(0, 10, (batch_size,), generator=gen).pin_memory()
-            inputs = inputs.to(args.gpu, non_blocking=True)                   # :97
-            labels = labels.to(args.gpu, non_blocking=True)                   # :98
+        if train is not None:
+            sampler_train.set_epoch(epoch)                                    # :92
+        for i, (inputs, labels) in enumerate(trainloader if train is not None else synthetic()):   # :94
             optimizer.zero_grad()                                             # :101
             outputs = net(inputs)                                             # :104
             loss = criterion(outputs, labels)                                 # :105
@@ -54,6 +84,12 @@ def main(args):
     print('Finished Training')
     if rank == 0 and args.save:
         torch.save(net.state_dict(), args.save)                               # :118-119 (single writer)
+    if test is not None:                                                      # :121-136
+        sampler_test = b2.DistributedSampler(test[0].shape[0], num_replicas=world, rank=rank, shuffle=False)
+        accuracy = b2.Accuracy(args.gpu)
+        for images, labels in b2.DeviceCifarLoader(test[0], test[1], batch_size, sampler_test, args.gpu):
+            accuracy.update(net(images), labels)          # batch-stat BatchNorm, as the reference never calls .eval()
+        print('Accuracy of the network on the 10000 test images: %d %%' % (100 * accuracy.compute()))
     if args.distributed:
         b2.destroy()
 
@@ -68,5 +104,6 @@ if __name__ == '__main__':
     parser.add_argument("--steps", type=int, default=200, help="synthetic mini-batches per epoch")
     parser.add_argument("--print-every", type=int, default=100)               # reference: 2000
     parser.add_argument("--seed", type=int, default=0)
+    parser.add_argument("--data", default="./data", help="root holding cifar-10-batches-py (synthetic input if absent)")
     parser.add_argument("--save", default="", help="path for state_dict (reference: ./cifar_net.pth)")
     main(parser.parse_args())

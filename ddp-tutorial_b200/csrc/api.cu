@@ -188,6 +188,21 @@ int b2_sgd(float *p, const float *g, float *m, int64_t n, float lr, float moment
     GUARD_END
 }
 
+// ---- input pipeline / eval -------------------------------------------------------
+int b2_preprocess_u8(const void *x_u8_nhwc, float *y_nchw, int N, int H, int W, int C, const float *mean3, const float *std3,
+                     void *stream) {
+    GUARD_BEGIN
+    B2_CHECK(x_u8_nhwc && y_nchw && mean3 && std3, B2_ERR_ARG, "b2_preprocess_u8: NULL argument");
+    return op_u8_to_normalized((const uint8_t *)x_u8_nhwc, y_nchw, N, H, W, C, mean3, std3, (cudaStream_t)stream);
+    GUARD_END
+}
+int b2_argmax_count(const float *logits, const int64_t *labels, int batch, int classes, long long *counts, void *stream) {
+    GUARD_BEGIN
+    B2_CHECK(logits && labels && counts, B2_ERR_ARG, "b2_argmax_count: NULL argument");
+    return op_argmax_count(logits, labels, batch, classes, counts, (cudaStream_t)stream);
+    GUARD_END
+}
+
 // ---- kernel-level test entry: one conv pass through the tcgen05 path or the SIMT path -------
 int b2_conv_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, int pad, int mode, int use_umma, int acc,
                  const void *x_bf16, const float *w_master, const void *dy_bf16, void *out, void *stream) {

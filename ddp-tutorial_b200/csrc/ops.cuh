@@ -99,6 +99,13 @@ int op_ce_loss_grad(const float *logits, const int64_t *labels, int B, int C, fl
 int op_sgd(float *p, const float *g, float *m, int64_t n, float lr, float momentum, float gscale,
            int first, bf16 *pb, cudaStream_t s);
 
+// ---- input pipeline / eval -------------------------------------------
+// uint8 HWC images [N][H][W][C] (CIFAR's on-disk layout) -> fp32 NCHW, ToTensor + Normalize(mean, std)
+// per channel: y = (x/255 - mean[c]) / std[c]   (cifar_example_ddp.py:61-63)
+int op_u8_to_normalized(const uint8_t *x, float *y, int N, int H, int W, int C, const float *mean3, const float *std3, cudaStream_t s);
+// counts[0] += #(argmax(logits[b]) == labels[b]), counts[1] += B   (first maximum wins, like torch.max)
+int op_argmax_count(const float *logits, const int64_t *labels, int B, int C, long long *counts, cudaStream_t s);
+
 // ---- communicator hooks used by the model's bucketed backward (comm.cu) ------------------
 bool comm_ready();
 int comm_allreduce_sgd_range(float *m, int64_t off, int64_t n, float lr, float momentum, int first, int algo, bf16 *mirror,

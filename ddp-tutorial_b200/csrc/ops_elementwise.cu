@@ -1021,3 +1021,53 @@ int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx,
 }
 
 }  // namespace b2
+
+// =====================================================================================
+// input pipeline / eval kernels
+// =====================================================================================
+namespace b2 {
+
+__global__ void __launch_bounds__(256)
+k_u8_to_normalized(const uint8_t *__restrict__ x, float *__restrict__ y, int N, int H, int W, int C, float m0, float m1, float m2,
+                   float s0, float s1, float s2) {
+    pdl_sync();
+    const int64_t total = (int64_t)N * C * H * W;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int w = i % W; int64_t r = i / W;
+        int h = r % H; r /= H;
+        int c = r % C; int n = (int)(r / C);
+        float v = (float)x[(((int64_t)n * H + h) * W + w) * C + c] / 255.0f;      // ToTensor
+        float m = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+        y[i] = (v - m) / sd;                                                       // Normalize
+    }
+}
+int op_u8_to_normalized(const uint8_t *x, float *y, int N, int H, int W, int C, const float *mean3, const float *std3, cudaStream_t s) {
+    B2_CHECK(C == 3, B2_ERR_UNSUPPORTED, "u8 preprocess: 3-channel images only");
+    int64_t total = (int64_t)N * C * H * W;
+    int blocks = (int)ceil_div(total, 256); if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    B2_LAUNCH(k_u8_to_normalized, blocks, 256, 0, s, x, y, N, H, W, C, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_argmax_count(const float *__restrict__ logits, const int64_t *__restrict__ labels, int B, int C, long long *counts) {
+    pdl_sync();
+    int correct = 0;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        const float *row = logits + (int64_t)b * C;
+        int best = 0; float bv = row[0];
+        for (int j = 1; j < C; ++j) if (row[j] > bv) { bv = row[j]; best = j; }
+        correct += (best == (int)labels[b]);
+    }
+    correct = __reduce_add_sync(0xffffffffu, correct);
+    if ((threadIdx.x & 31) == 0 && correct) atomicAdd((unsigned long long *)counts, (unsigned long long)correct);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long *)counts + 1, (unsigned long long)B);
+}
+int op_argmax_count(const float *logits, const int64_t *labels, int B, int C, long long *counts, cudaStream_t s) {
+    B2_CHECK(B > 0 && C > 0, B2_ERR_ARG, "argmax_count: empty batch");
+    int blocks = (int)ceil_div(B, 256); if (blocks > 64) blocks = 64;
+    B2_LAUNCH(k_argmax_count, blocks, 256, 0, s, logits, labels, B, C, counts);
+    return 0;
+}
+
+}  // namespace b2

@@ -121,6 +121,16 @@ int b2_conv_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, int p
                  int use_umma, int acc, const void *x_bf16, const float *w_master,
                  const void *dy_bf16, void *out, void *stream);
 
+/* ---- next rows: input transform and eval counters -----------------------------
+ * transforms.ToTensor() + Normalize(mean, std) (cifar_example_ddp.py:61-63) on the device:
+ * uint8 [N][H][W][3] (HWC, host values 0..255) -> fp32 NCHW.  mean3/std3 are HOST pointers. */
+int b2_preprocess_u8(const void *x_u8_nhwc, float *y_nchw, int N, int H, int W, int C,
+                     const float *mean3, const float *std3, void *stream);
+/* eval loop body (cifar_example_ddp.py:131-133): counts[0] += correct top-1, counts[1] += batch;
+ * counts is a device int64[2] the caller zeroes once. */
+int b2_argmax_count(const float *logits, const int64_t *labels, int batch, int classes,
+                    long long *counts, void *stream);
+
 /* ---- criterion: nn.CrossEntropyLoss() fwd+bwd (cifar_example_ddp.py:85,105) -- */
 int b2_ce_loss_grad(const float *logits, const int64_t *labels, int batch, int classes,
                     float *loss_out, float *dlogits, void *stream);

@@ -105,3 +105,18 @@ def test_optimizer_rejects_foreign_parameters():
         b2.SGD([torch.zeros(3)], lr=0.1)
     with pytest.raises(b2.B2Error):
         b2.SGD([], lr=0.1)
+
+
+@pytest.mark.parametrize("n,world,shuffle,drop_last", [(50000, 8, True, False), (10000, 8, False, False), (103, 4, True, False),
+                                                         (103, 4, True, True), (7, 8, True, False), (64, 1, True, False)])
+def test_distributed_sampler_matches_torch(n, world, shuffle, drop_last):
+    """Index stream identical to torch.utils.data.DistributedSampler (cifar_example_ddp.py:70,92)."""
+    from torch.utils.data.distributed import DistributedSampler as TorchSampler
+    ds = list(range(n))
+    for rank in (0, world - 1):
+        ref = TorchSampler(ds, num_replicas=world, rank=rank, shuffle=shuffle, seed=3, drop_last=drop_last)
+        mine = b2.DistributedSampler(n, num_replicas=world, rank=rank, shuffle=shuffle, seed=3, drop_last=drop_last)
+        for epoch in (0, 1, 5):
+            ref.set_epoch(epoch); mine.set_epoch(epoch)
+            assert list(ref) == list(mine)
+            assert len(ref) == len(mine)
