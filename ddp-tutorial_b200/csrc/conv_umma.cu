@@ -101,11 +101,14 @@ static bool tap_alive(int d, int step, int nbox, int src) {
 // =================================================================================
 // device: fprop / dgrad
 // =================================================================================
-constexpr int kStagesTap = 4;
 constexpr int kATileBytes = 128 * 128;       // 128 pixel rows x 64 bf16
 constexpr int kBTileBytes = 64 * 128;        // 64 channel rows x 64 bf16
-constexpr int kTapSmem = kStagesTap * (kATileBytes + kBTileBytes) + 1024 /*align*/ + 256 /*barriers*/;
+// Pipeline depth: the per-SM load rate is bytes-in-flight / L2 latency, so a grid that gives each SM
+// one CTA needs a deep ring (8 stages = 192 KB in flight); grids with >= 2 CTAs per SM use 4 stages
+// (96 KB each) so that two CTAs co-reside and overlap one's epilogue with the other's main loop.
+constexpr int tap_smem(int stages) { return stages * (kATileBytes + kBTileBytes) + 1024 /*align*/ + 256 /*barriers*/; }
 
+template <int kStagesTap>
 __global__ void __launch_bounds__(192)
 k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
           const __grid_constant__ TapGemmParams p) {
@@ -370,7 +373,8 @@ k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUten
 // =================================================================================
 static std::once_flag g_attr_once;
 static void set_attrs() {
-    cudaFuncSetAttribute(k_tapgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, kTapSmem);
+    cudaFuncSetAttribute(k_tapgemm<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tap_smem(4));
+    cudaFuncSetAttribute(k_tapgemm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tap_smem(8));
     cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
 }
 
@@ -440,7 +444,9 @@ int umma_plan_dgrad(const ConvGeom &g, const bf16 *dy, const bf16 *w, bf16 *dx, 
 int umma_conv_launch(const UmmaConvPlan &plan, cudaStream_t s) {
     B2_CHECK(plan.valid, B2_ERR_STATE, "umma conv: plan not valid");
     std::call_once(g_attr_once, set_attrs);
-    B2_LAUNCH(k_tapgemm, plan.grid, 192, kTapSmem, s, plan.a_map, plan.b_map, plan.p);
+    const unsigned ctas = plan.grid.x * plan.grid.y * plan.grid.z;
+    if (ctas <= (unsigned)kNumSMs) { B2_LAUNCH(k_tapgemm<8>, plan.grid, 192, tap_smem(8), s, plan.a_map, plan.b_map, plan.p); }
+    else { B2_LAUNCH(k_tapgemm<4>, plan.grid, 192, tap_smem(4), s, plan.a_map, plan.b_map, plan.p); }
     return 0;
 }
 
