@@ -15,6 +15,8 @@
 //   wgrad (k_wgrad): dW[co][k] += dY[pix][co]^T * X_tap[pix][k]: both operands MN-major
 //       (the contraction runs over pixels, i.e. over tile rows), split over pixel tiles.
 #include <mutex>
+#include <algorithm>
+#include <stdlib.h>
 #include "conv_umma.cuh"
 #include "umma.cuh"
 
@@ -106,9 +108,15 @@ constexpr int kBTileBytes = 64 * 128;        // 64 channel rows x 64 bf16
 // Pipeline depth: the per-SM load rate is bytes-in-flight / L2 latency, so a grid that gives each SM
 // one CTA needs a deep ring (8 stages = 192 KB in flight); grids with >= 2 CTAs per SM use 4 stages
 // (96 KB each) so that two CTAs co-reside and overlap one's epilogue with the other's main loop.
-constexpr int tap_smem(int stages) { return stages * (kATileBytes + kBTileBytes) + 1024 /*align*/ + 256 /*barriers*/; }
+// SPLIT: a cluster of two CTAs shares one output tile, each running half of the K steps (doubles the
+// number of SMs pulling operands for layers whose grid is smaller than the chip); CTA 1 hands its
+// fp32 accumulators to CTA 0 through distributed shared memory, CTA 0 runs the epilogue.
+constexpr int kSplitStageBytes = 128 * 68 * 4;      // [128 rows][64 + 4 pad] fp32
+constexpr int tap_smem(int stages, bool split = false) {
+    return stages * (kATileBytes + kBTileBytes) + (split ? kSplitStageBytes : 0) + 1024 /*align*/ + 256 /*barriers*/;
+}
 
-template <int kStagesTap>
+template <int kStagesTap, bool SPLIT>
 __global__ void __launch_bounds__(192)
 k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
           const __grid_constant__ TapGemmParams p) {
@@ -116,15 +124,20 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
     uint8_t *sB = smem + kStagesTap * kATileBytes;
-    uint64_t *bars = (uint64_t *)(sB + kStagesTap * kBTileBytes);
+    float *sX = (float *)(sB + kStagesTap * kBTileBytes);                 // SPLIT: partner's accumulators land here
+    uint64_t *bars = (uint64_t *)((uint8_t *)sX + (SPLIT ? kSplitStageBytes : 0));
     uint64_t *full = bars, *empty = bars + kStagesTap, *tmem_full = bars + 2 * kStagesTap;
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * kStagesTap + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TapClass &cls = p.cls[blockIdx.z];
-    const int n_blk = blockIdx.x / p.h_blocks, h_blk = blockIdx.x % p.h_blocks;
+    const uint32_t crank = SPLIT ? cluster_ctarank() : 0u;
+    const int tile_x = SPLIT ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_blk = tile_x / p.h_blocks, h_blk = tile_x % p.h_blocks;
     const int ch0 = blockIdx.y * 64;
-    const int ksteps = cls.ntaps * p.c_chunks;
+    const int ksteps_all = cls.ntaps * p.c_chunks;
+    const int ks_begin = SPLIT ? (crank == 0 ? 0 : (ksteps_all + 1) / 2) : 0;
+    const int ks_end = SPLIT ? (crank == 0 ? (ksteps_all + 1) / 2 : ksteps_all) : ksteps_all;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&a_map); prefetch_tmap(&b_map);
@@ -143,7 +156,7 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int ks = 0; ks < ksteps; ++ks) {
+            for (int ks = ks_begin; ks < ks_end; ++ks) {
                 const int tap = ks / p.c_chunks, cc = ks - tap * p.c_chunks;
                 mbar_wait(&empty[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&full[stage], kATileBytes + kBTileBytes);
@@ -159,14 +172,14 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
             const uint32_t idesc = make_idesc_bf16(128, 64, 0, p.b_mn);
             const uint32_t bstep = p.b_mn ? 2048 : 32;     // 16 K-rows of 128 B vs 16 K-elements
             int stage = 0; uint32_t phase = 0;
-            for (int ks = 0; ks < ksteps; ++ks) {
+            for (int ks = ks_begin; ks < ks_end; ++ks) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(sA + stage * kATileBytes), b0 = smem_u32(sB + stage * kBTileBytes);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     mma_bf16_ss(tmem_base, make_desc_sw128(a0 + k * 32, 16, 1024),
-                                make_desc_sw128(b0 + k * bstep, kBTileBytes, 1024), idesc, (ks | k) != 0);
+                                make_desc_sw128(b0 + k * bstep, kBTileBytes, 1024), idesc, (ks > ks_begin || k > 0) ? 1u : 0u);
                 }
                 mma_commit(&empty[stage]);
                 if (++stage == kStagesTap) { stage = 0; phase ^= 1; }
@@ -186,6 +199,22 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         uint32_t v[32];
+        if (SPLIT && crank == 1) {
+            // hand this CTA's partial accumulators to CTA 0 (its sX), then leave through the cluster barrier
+            const uint32_t remote = map_to_cta(smem_u32(sX), 0) + (uint32_t)r * 68 * 4;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + half * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    st_cluster_f4(remote + (half * 32 + j * 4) * 4, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+            cluster_arrive();
+            cluster_wait();
+        } else {
+        if (SPLIT) { cluster_arrive(); cluster_wait(); }       // partner's accumulators are in sX now
         float *sT = (float *)sA;                       // [128][65] fp32 staging for per-channel sums
         float *sT2 = sT + 128 * 65;                    // second plane (spills into the B stages: 66.5 KB < 96 KB)
         const bool want_fwd = p.stats != nullptr, want_bwd = p.bn_bsum != nullptr;
@@ -200,6 +229,11 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
                 float f[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
+                if (SPLIT) {
+                    const float4 x0 = *(const float4 *)(sX + r * 68 + half * 32 + j * 8);
+                    const float4 x1 = *(const float4 *)(sX + r * 68 + half * 32 + j * 8 + 4);
+                    f[0] += x0.x; f[1] += x0.y; f[2] += x0.z; f[3] += x0.w; f[4] += x1.x; f[5] += x1.y; f[6] += x1.z; f[7] += x1.w;
+                }
                 if (p.acc) {
                     uint4 old = d4[j];
                     const __nv_bfloat162 *o2 = (const __nv_bfloat162 *)&old;
@@ -252,8 +286,10 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
             atomicAdd(st + ch0 + c, s0);
             atomicAdd(st + p.out_C + ch0 + c, s1);
         }
+        }   // !(SPLIT && crank == 1)
         tc_fence_before();
     }
+    if (SPLIT && warp < 2) { cluster_arrive(); cluster_wait(); }      // every thread of both CTAs joins the barrier once
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
 }
@@ -373,8 +409,9 @@ k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUten
 // =================================================================================
 static std::once_flag g_attr_once;
 static void set_attrs() {
-    cudaFuncSetAttribute(k_tapgemm<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tap_smem(4));
-    cudaFuncSetAttribute(k_tapgemm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tap_smem(8));
+    cudaFuncSetAttribute(k_tapgemm<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tap_smem(4));
+    cudaFuncSetAttribute(k_tapgemm<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tap_smem(8));
+    cudaFuncSetAttribute(k_tapgemm<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tap_smem(6, true));
     cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
 }
 
@@ -445,8 +482,20 @@ int umma_conv_launch(const UmmaConvPlan &plan, cudaStream_t s) {
     B2_CHECK(plan.valid, B2_ERR_STATE, "umma conv: plan not valid");
     std::call_once(g_attr_once, set_attrs);
     const unsigned ctas = plan.grid.x * plan.grid.y * plan.grid.z;
-    if (ctas <= (unsigned)kNumSMs) { B2_LAUNCH(k_tapgemm<8>, plan.grid, 192, tap_smem(8), s, plan.a_map, plan.b_map, plan.p); }
-    else { B2_LAUNCH(k_tapgemm<4>, plan.grid, 192, tap_smem(4), s, plan.a_map, plan.b_map, plan.p); }
+    int min_ksteps = 1 << 30;
+    for (int c = 0; c < plan.p.nclasses; ++c) min_ksteps = std::min(min_ksteps, plan.p.cls[c].ntaps * plan.p.c_chunks);
+    // measured (r01): parity-green but 4% slower end to end (1.051 vs 1.007 ms/step) -- the extra
+    // cluster barrier / DSMEM hand-off and the competition with the concurrent wgrad stream outweigh
+    // the additional SMs.  Kept behind B2_SPLITK=1 for layer-level experiments.
+    static const bool allow_split = [] { const char *e = getenv("B2_SPLITK"); return e && e[0] == '1'; }();
+    if (allow_split && ctas <= (unsigned)kNumSMs && min_ksteps >= 4) {
+        // split-K cluster pair: twice the CTAs (and SMs) per output tile
+        dim3 g(plan.grid.x * 2, plan.grid.y, plan.grid.z);
+        cudaError_t e = launch_kernel_cluster(k_tapgemm<6, true>, g, dim3(192), (size_t)tap_smem(6, true), s, 2u, plan.a_map, plan.b_map, plan.p);
+        ++g_launches;
+        B2_CHECK(e == cudaSuccess, B2_ERR_CUDA, "k_tapgemm<split> launch failed: %s", cudaGetErrorString(e));
+    } else if (ctas <= (unsigned)kNumSMs) { B2_LAUNCH((k_tapgemm<8, false>), plan.grid, 192, tap_smem(8), s, plan.a_map, plan.b_map, plan.p); }
+    else { B2_LAUNCH((k_tapgemm<4, false>), plan.grid, 192, tap_smem(4), s, plan.a_map, plan.b_map, plan.p); }
     return 0;
 }
 
