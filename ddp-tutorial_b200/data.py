@@ -112,3 +112,58 @@ class Accuracy:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(c)
         return float(c[0]) / max(1.0, float(c[1]))
+
+
+class DevicePrefetcher:
+    """Overlaps the host->device copy of batch i+1 with the training step on batch i (what the
+    reference gets from ``DataLoader`` worker prefetch + ``.to(gpu)``, cifar_example_ddp.py:94-98).
+
+    Wraps any iterable of ``(inputs, labels)`` host tensors (pinned memory for a truly asynchronous
+    copy).  Each batch is copied on a private copy stream into one of ``depth`` persistent device
+    slots (stable addresses, so the model's captured CUDA graphs are re-used), and the consumer's
+    stream waits on the copy's event before using it."""
+
+    def __init__(self, iterable, device, depth: int = 2):
+        self.it, self.device, self.depth = iterable, torch.device("cuda", device) if isinstance(device, int) else torch.device(device), depth
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = []
+
+    def _slot(self, k, x, y):
+        if len(self.slots) <= k or self.slots[k][0].shape != x.shape:
+            s = (torch.empty(x.shape, dtype=x.dtype, device=self.device), torch.empty(y.shape, dtype=y.dtype, device=self.device),
+                 torch.cuda.Event(), torch.cuda.Event())
+            if len(self.slots) <= k:
+                self.slots.append(s)
+            else:
+                self.slots[k] = s
+        return self.slots[k]
+
+    def __iter__(self):
+        it = iter(self.it)
+        pending = []
+        k = 0
+
+        def enqueue():
+            nonlocal k
+            try:
+                x, y = next(it)
+            except StopIteration:
+                return False
+            dx, dy, copied, consumed = self._slot(k % self.depth, x, y)
+            self.stream.wait_event(consumed)               # the step that last used this slot is done with it
+            with torch.cuda.stream(self.stream):
+                dx.copy_(x, non_blocking=True); dy.copy_(y, non_blocking=True)
+                copied.record(self.stream)
+            pending.append((dx, dy, copied, consumed))
+            k += 1
+            return True
+
+        for _ in range(self.depth):
+            if not enqueue():
+                break
+        while pending:
+            dx, dy, copied, consumed = pending.pop(0)
+            torch.cuda.current_stream(self.device).wait_event(copied)
+            yield dx, dy
+            consumed.record(torch.cuda.current_stream(self.device))   # work enqueued so far has consumed the slot
+            enqueue()

@@ -341,3 +341,15 @@ def test_checkpoint_round_trip_into_reference_modules(tmp_path):
         theirs = ref(x)
     np.testing.assert_allclose(ours.numpy(), theirs.numpy(), rtol=1e-3, atol=1e-4)
     assert int(ref.bn1.num_batches_tracked) == 2          # one forward here + one in the reference check
+
+
+def test_device_prefetcher_delivers_batches_in_order():
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.randn(4, 3, 32, 32, generator=g).pin_memory(), torch.randint(0, 10, (4,), generator=g).pin_memory())
+               for _ in range(7)]
+    got = []
+    for x, y in b2.DevicePrefetcher(batches, DEV, depth=2):
+        got.append((x.cpu().clone(), y.cpu().clone()))     # the slot is recycled after the next yield
+    assert len(got) == 7
+    for (x, y), (rx, ry) in zip(got, batches):
+        assert torch.equal(x, rx) and torch.equal(y, ry)
