@@ -149,6 +149,12 @@ int b2_model_profile_collect(b2_model *h, double *ms, double *flops, double *byt
     return h->m->prof_collect(ms, flops, bytes, launches);
     GUARD_END
 }
+int b2_model_time_conv_kernels(b2_model *h, int iters, double *ms3, double *flops3, int *launches3, void *stream) {
+    GUARD_BEGIN
+    B2_CHECK(h && ms3 && flops3 && launches3 && iters > 0, B2_ERR_ARG, "time_conv_kernels: bad arguments");
+    return h->m->time_conv_kernels(iters, ms3, flops3, launches3, (cudaStream_t)stream);
+    GUARD_END
+}
 int b2_model_num_ops(const b2_model *h) { return h ? (int)h->m->ops.size() : 0; }
 int b2_model_read_activation(b2_model *h, int op, int want_grad, float *out, int64_t capacity, int64_t *numel,
                              int shape[4], void *stream) {

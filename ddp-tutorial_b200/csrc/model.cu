@@ -391,6 +391,32 @@ int Model::prof_collect(double ms[PC_COUNT], double flops[PC_COUNT], double byte
     return 0;
 }
 
+int Model::time_conv_kernels(int iters, double ms[3], double flops[3], int launches[3], cudaStream_t s) {
+    B2_CHECK(plans_ready, B2_ERR_STATE, "time_conv_kernels: run a forward first");
+    for (int i = 0; i < 3; ++i) { ms[i] = 0; flops[i] = 0; launches[i] = 0; }
+    cudaEvent_t a, b;
+    B2_CUDA(cudaEventCreate(&a)); B2_CUDA(cudaEventCreate(&b));
+    auto timed = [&](int cls, double fl, auto &&launch) -> int {
+        for (int w = 0; w < 2; ++w) B2_TRY(launch());
+        B2_CUDA(cudaEventRecord(a, s));
+        for (int it = 0; it < iters; ++it) B2_TRY(launch());
+        B2_CUDA(cudaEventRecord(b, s));
+        B2_CUDA(cudaEventSynchronize(b));
+        float t = 0.f;
+        B2_CUDA(cudaEventElapsedTime(&t, a, b));
+        ms[cls] += t / iters; flops[cls] += fl; launches[cls] += 1;
+        return 0;
+    };
+    for (Op &o : ops) {
+        if (o.type != OP_CONV || !(o.use_umma || o.stem_umma)) continue;
+        B2_TRY(timed(0, o.fplan.flops, [&] { return umma_conv_launch(o.fplan, s); }));
+        if (o.use_umma && o.need_dgrad) B2_TRY(timed(1, o.dplan.flops, [&] { return umma_conv_launch(o.dplan, s); }));
+        B2_TRY(timed(2, o.wplan.flops, [&] { return umma_wgrad_launch(o.wplan, s); }));
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return 0;
+}
+
 // =================================================================================
 // execution
 // =================================================================================

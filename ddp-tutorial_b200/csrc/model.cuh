@@ -101,6 +101,9 @@ struct Model {
     int prof_begin(int cat, double flops, double bytes, cudaStream_t s);
     void prof_end(int h, cudaStream_t s);
     int prof_collect(double ms[PC_COUNT], double flops[PC_COUNT], double bytes[PC_COUNT], int launches[PC_COUNT]);
+    // per-class (fprop, dgrad, wgrad) average kernel duration of the tcgen05 conv launches of one
+    // step: every plan is launched `iters` times back to back between two events
+    int time_conv_kernels(int iters, double ms[3], double flops[3], int launches[3], cudaStream_t s);
 
     static int create(int kind, int batch, int num_classes, int precision, int device, Model **out);
     ~Model();

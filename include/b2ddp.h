@@ -108,6 +108,11 @@ int b2_model_set_graphs(b2_model *m, int enable);
 #define B2_PROF_COUNT 7
 int b2_model_profile(b2_model *m, int enable);
 int b2_model_profile_collect(b2_model *m, double *ms, double *flops, double *bytes, int *launches);
+/* roofline leg: average duration of every tcgen05 conv launch of one step (each plan launched
+ * `iters` times back to back between two CUDA events on `stream`), summed per class
+ * [0]=fprop [1]=dgrad [2]=wgrad, with the FLOPs those launches execute.  Clobbers gradients. */
+int b2_model_time_conv_kernels(b2_model *m, int iters, double *ms3, double *flops3, int *launches3,
+                               void *stream);
 /* debugging / parity: copy an internal activation (by op index) out as fp32 NCHW */
 int b2_model_num_ops(const b2_model *m);
 int b2_model_read_activation(b2_model *m, int op, int want_grad, float *out, int64_t capacity,
