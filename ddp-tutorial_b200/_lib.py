@@ -68,6 +68,7 @@ _SIGS = {
     "b2_allreduce_sgd": (_i, [_vp, _i64, _f, _f, _i, _i, _vp, _vp]),
     "b2_allreduce_sgd_range": (_i, [_vp, _i64, _i64, _f, _f, _i, _i, _vp, _vp]),
     "b2_model_set_ddp": (_i, [_vp, _i, _vp, _f, _f, _i, _i64]),
+    "b2_model_set_fused_sgd": (_i, [_vp, _i, _vp, _f, _f, _i64]),
     "b2_model_ddp_first_step": (_i, [_vp, _i]),
     "b2_model_num_buckets": (_i, [_vp]),
     "b2_graph_begin": (_i, [_vp]),

@@ -129,7 +129,13 @@ int b2_model_set_graphs(b2_model *h, int enable) {
 int b2_model_set_ddp(b2_model *h, int enable, float *momentum_buf, float lr, float momentum, int algo, int64_t bucket_elems) {
     GUARD_BEGIN
     B2_CHECK(h, B2_ERR_ARG, "NULL model");
-    return h->m->set_ddp(enable != 0, momentum_buf, lr, momentum, algo, bucket_elems);
+    return h->m->set_ddp(enable != 0, momentum_buf, lr, momentum, algo, bucket_elems, false);
+    GUARD_END
+}
+int b2_model_set_fused_sgd(b2_model *h, int enable, float *momentum_buf, float lr, float momentum, int64_t bucket_elems) {
+    GUARD_BEGIN
+    B2_CHECK(h, B2_ERR_ARG, "NULL model");
+    return h->m->set_ddp(enable != 0, momentum_buf, lr, momentum, 0, bucket_elems, true);
     GUARD_END
 }
 int b2_model_ddp_first_step(b2_model *h, int first) {

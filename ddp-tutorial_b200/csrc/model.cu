@@ -337,12 +337,13 @@ void Model::compute_buckets(int64_t bucket_elems) {
     if (emitted > 0) buckets.push_back(Bucket{0, emitted, 0});
 }
 
-int Model::set_ddp(bool enable, float *mom, float lr, float momentum, int algo, int64_t bucket_elems) {
+int Model::set_ddp(bool enable, float *mom, float lr, float momentum, int algo, int64_t bucket_elems, bool local) {
     drop_graphs();
     eager_runs_bwd = 0;
     ddp_on = false;
     if (!enable) return 0;
-    B2_CHECK(comm_ready(), B2_ERR_STATE, "set_ddp: communicator not initialised / no buffers registered");
+    ddp_local = local;
+    B2_CHECK(local || comm_ready(), B2_ERR_STATE, "set_ddp: communicator not initialised / no buffers registered");
     B2_CHECK(mom, B2_ERR_ARG, "set_ddp: NULL momentum buffer");
     ddp_mom = mom; ddp_lr = lr; ddp_momentum = momentum; ddp_algo = algo;
     if (!ddp_stream) {
@@ -645,8 +646,12 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
                 B2_CUDA(cudaEventRecord(wg_join, wg_stream));
                 B2_CUDA(cudaStreamWaitEvent(ddp_stream, wg_join, 0));
             }
-            B2_TRY(comm_allreduce_sgd_range(ddp_mom, bk.off, bk.n, ddp_lr, ddp_momentum, ddp_first, ddp_algo,
-                                            p_params_bf16, ddp_stream));
+            if (ddp_local)
+                B2_TRY(op_sgd(p_params + bk.off, p_grads + bk.off, ddp_mom + bk.off, bk.n, ddp_lr, ddp_momentum, 1.f, ddp_first,
+                              p_params_bf16 ? p_params_bf16 + bk.off : nullptr, ddp_stream));
+            else
+                B2_TRY(comm_allreduce_sgd_range(ddp_mom, bk.off, bk.n, ddp_lr, ddp_momentum, ddp_first, ddp_algo,
+                                                p_params_bf16, ddp_stream));
             forked = true;
         }
         return 0;
@@ -680,7 +685,8 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
             const double cflops = 2.0 * o.g.M() * o.g.Co * o.g.K();
             const double cbytes = ti.numel * (double)dt_size(ti.dt) + to.numel * (double)dt_size(to.dt);
             int ph = prof_begin(PC_CONV_WGRAD, o.use_umma ? o.wplan.flops : cflops, cbytes + (double)o.g.Co * o.g.K() * 4, s);
-            {
+            static const bool dbg_skip_wgrad = [] { const char *e = getenv("B2_DEBUG_SKIP_WGRAD"); return e && e[0] == '1'; }();
+            if (!dbg_skip_wgrad) {      // (timing experiments only: B2_DEBUG_SKIP_WGRAD=1 leaves stale weight gradients)
                 cudaStream_t ws = wgrad_stream();
                 if (o.use_umma) B2_TRY(umma_wgrad_launch(o.wplan, ws));
                 else B2_TRY(conv_simt_wgrad(o.g, ti.val, to.grad, ti.dt, p_grads + o.w_off, wgrad_ws, wgrad_floats, ws));

@@ -84,6 +84,7 @@ struct Model {
     struct Bucket { int64_t off, n; int after_op; };   // launch after ops[after_op] has run backward
     std::vector<Bucket> buckets;
     bool ddp_on = false;
+    bool ddp_local = false;          // world size 1: the bucketed update is the plain SGD kernel (no exchange)
     float *ddp_mom = nullptr; float ddp_lr = 0.f, ddp_momentum = 0.f; int ddp_algo = 0, ddp_first = 1;
     // weight gradients are off the backward critical path (only the optimizer consumes them):
     // they run on their own stream, forked after each layer's dY is final, joined at the end
@@ -92,7 +93,7 @@ struct Model {
     bool wgrad_async = true;
     cudaStream_t ddp_stream = nullptr;
     cudaEvent_t ddp_fork = nullptr, ddp_join = nullptr;
-    int set_ddp(bool enable, float *mom, float lr, float momentum, int algo, int64_t bucket_elems);
+    int set_ddp(bool enable, float *mom, float lr, float momentum, int algo, int64_t bucket_elems, bool local);
     void compute_buckets(int64_t bucket_elems);
     int64_t steps_tracked = 0;
     bool profiling = false;

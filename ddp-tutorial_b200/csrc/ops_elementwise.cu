@@ -602,32 +602,26 @@ int op_maxpool_backward_bf16x8(const bf16 *dy, const uint8_t *idx, bf16 *dx, int
     return 0;
 }
 
-// ---- stem im2col.  One block per (image, output row): the KS input rows x CH channels the row
-// needs are staged in shared memory with coalesced loads, then every thread emits 16-byte
-// chunks of the bf16 im2col rows (column order (kh, kw, c), zero beyond KS*KS*CH).
+// ---- stem im2col.  One block per image: the whole fp32 image (CH x H x W, 12 KB for CIFAR) is
+// staged in shared memory with coalesced loads, then every thread emits 16-byte chunks of the
+// bf16 im2col rows (column order (kh, kw, c), zero beyond KS*KS*CH).
 template <int KS, int CH>
 __global__ void __launch_bounds__(256)
 k_stem_im2col(const float *__restrict__ x, bf16 *__restrict__ col, int N, int H, int W, int stride, int pad,
               int Ho, int Wo, int kpad) {
     pdl_sync();
-    extern __shared__ float srow[];                 // [KS][CH][W + 2*pad]  (zero padded left/right)
-    const int Wp = W + 2 * pad;
-    const int n = blockIdx.x / Ho, ho = blockIdx.x - n * Ho;
-    const float *xn = x + (int64_t)n * CH * H * W;
-    for (int i = threadIdx.x; i < KS * CH * Wp; i += blockDim.x) {
-        const int wp = i % Wp; const int t = i / Wp;
-        const int c = t % CH, kh = t / CH;
-        const int hi = ho * stride - pad + kh, wi = wp - pad;
-        float v = 0.f;
-        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = xn[((int64_t)c * H + hi) * W + wi];
-        srow[i] = v;
-    }
+    extern __shared__ float simg[];                 // [CH][H][W]
+    const int n = blockIdx.x;
+    const float4 *src = (const float4 *)(x + (int64_t)n * CH * H * W);
+    for (int i = threadIdx.x; i < CH * H * W / 4; i += blockDim.x) ((float4 *)simg)[i] = src[i];
     __syncthreads();
     constexpr int K = KS * KS * CH;
     const int chunks = kpad >> 3;
-    bf16 *orow = col + ((int64_t)n * Ho + ho) * Wo * kpad;
-    for (int i = threadIdx.x; i < Wo * chunks; i += blockDim.x) {
-        const int ch = i % chunks, wo = i / chunks;
+    bf16 *obase = col + (int64_t)n * Ho * Wo * kpad;
+    const int items = Ho * Wo * chunks;
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int ch = i % chunks, pix = i / chunks;
+        const int ho = pix / Wo, wo = pix - ho * Wo;
         __align__(16) bf16 o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -636,19 +630,20 @@ k_stem_im2col(const float *__restrict__ x, bf16 *__restrict__ col, int N, int H,
             if (kk < K) {
                 const int tap = kk / CH, c = kk - tap * CH;
                 const int kh = tap / KS, kw = tap - kh * KS;
-                v = srow[(kh * CH + c) * Wp + wo * stride + kw];
+                const int hi = ho * stride - pad + kh, wi = wo * stride - pad + kw;
+                if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = simg[(c * H + hi) * W + wi];
             }
             o[e] = __float2bfloat16_rn(v);
         }
-        *(uint4 *)(orow + (int64_t)wo * kpad + ch * 8) = *(uint4 *)o;
+        *(uint4 *)(obase + (int64_t)pix * kpad + ch * 8) = *(uint4 *)o;
     }
 }
 int op_stem_im2col(const float *x_nchw, bf16 *col, int N, int C, int H, int W, int k, int stride, int pad, int Ho, int Wo,
                    int kpad, cudaStream_t s) {
     B2_CHECK(kpad % 8 == 0 && kpad >= k * k * C, B2_ERR_ARG, "stem im2col: bad kpad %d", kpad);
-    B2_CHECK(k == 7 && C == 3, B2_ERR_UNSUPPORTED, "stem im2col: only the 7x7 / 3-channel ResNet stem is instantiated");
-    size_t smem = (size_t)k * C * (W + 2 * pad) * sizeof(float);
-    B2_LAUNCH((k_stem_im2col<7, 3>), N * Ho, 256, smem, s, x_nchw, col, N, H, W, stride, pad, Ho, Wo, kpad);
+    B2_CHECK(k == 7 && C == 3 && (C * H * W) % 4 == 0, B2_ERR_UNSUPPORTED, "stem im2col: only the 7x7 / 3-channel ResNet stem is instantiated");
+    size_t smem = (size_t)C * H * W * sizeof(float);
+    B2_LAUNCH((k_stem_im2col<7, 3>), N, 256, smem, s, x_nchw, col, N, H, W, stride, pad, Ho, Wo, kpad);
     return 0;
 }
 

@@ -122,6 +122,8 @@ class Engine:
                 self._bind(m)
             if self.ddp is not None and self.optimizer is not None and self.ddp.overlap:
                 self.ddp._configure_model(m, self.optimizer)
+            elif self.ddp is None and self.optimizer is not None and self.optimizer.fuse_into_backward:
+                self.optimizer._configure_model(m)
             self.models[batch] = m
         return m
 
@@ -215,6 +217,8 @@ class Engine:
         m = self._model(self._last_batch)
         if self.ddp is not None:
             self.ddp._before_backward(m)
+        elif self.optimizer is not None and self.optimizer.fuse_into_backward:
+            self.optimizer._before_backward(m)
         call("b2_backward", m.h, C.c_void_p(dlogits.data_ptr()), _stream_ptr())
         if self.ddp is not None:
             self.ddp._after_backward()

@@ -15,7 +15,8 @@ from .engine import _stream_ptr
 
 class SGD:
     def __init__(self, params, lr: float = 1e-3, momentum: float = 0.0, dampening: float = 0.0,
-                 weight_decay: float = 0.0, nesterov: bool = False):
+                 weight_decay: float = 0.0, nesterov: bool = False, fuse_into_backward: bool = True,
+                 bucket_cap_mb: float = 32.0):
         if dampening != 0.0 or weight_decay != 0.0 or nesterov:
             raise B2Error("only the reference's configuration (lr, momentum) is implemented")
         params = list(params)
@@ -31,9 +32,27 @@ class SGD:
         self.lr, self.momentum = float(lr), float(momentum)
         self.state_steps = 0
         self.momentum_buffer = torch.zeros_like(engine.flat_params)
+        # fuse_into_backward (default): the update of a gradient bucket is launched from inside
+        # backward() on a side stream as soon as the bucket is complete, so most of the optimizer
+        # pass runs under the rest of backward and step() only does bookkeeping (parameters are
+        # already updated when backward() returns).  False: one pass over the flat vectors at step().
+        self.fuse_into_backward = fuse_into_backward
+        self.bucket_elems = int(bucket_cap_mb * (1 << 20) / 4)
+        self._fused_pending = False
         engine.optimizer = self
         if engine.ddp is not None:
             engine.ddp._attach_optimizer(self)
+        elif fuse_into_backward:
+            for m in engine.models.values():
+                self._configure_model(m)
+
+    def _configure_model(self, m):
+        call("b2_model_set_fused_sgd", m.h, 1, C.c_void_p(self.momentum_buffer.data_ptr()), self.lr, self.momentum,
+             self.bucket_elems)
+
+    def _before_backward(self, m):
+        call("b2_model_ddp_first_step", m.h, 1 if self.state_steps == 0 else 0)
+        self._fused_pending = True
 
     def zero_grad(self, set_to_none: bool = True):
         """Gradients live in the flat bucket and are fully overwritten by every backward
@@ -45,6 +64,14 @@ class SGD:
         first = 1 if self.state_steps == 0 else 0
         if e.ddp is not None:
             e.ddp._optimizer_step(self, first)
+        elif self.fuse_into_backward:
+            if not self._fused_pending:
+                raise B2Error("optimizer.step() without a preceding backward()")
+            self._fused_pending = False            # the update already ran inside backward()
+            if e.flat_params_bf16 is not None:
+                e.mark_weights_clean()
+            else:
+                e.mark_weights_dirty()
         else:
             mirror = e.flat_params_bf16
             call("b2_sgd", C.c_void_p(e.flat_params.data_ptr()), C.c_void_p(e.flat_grads.data_ptr()),

@@ -191,6 +191,10 @@ int b2_allreduce_sgd_range(float *m, int64_t offset, int64_t n_elems, float lr, 
  * launch.  momentum: fp32 [param_count].  enable=0 restores the plain backward. */
 int b2_model_set_ddp(b2_model *m, int enable, float *momentum_buf, float lr, float momentum, int algo,
                      int64_t bucket_elems);
+/* single process: same bucketing, the per-bucket kernel is the plain SGD-momentum update (no exchange):
+ * the optimizer pass of the first (largest) buckets runs under the rest of backward. */
+int b2_model_set_fused_sgd(b2_model *m, int enable, float *momentum_buf, float lr, float momentum,
+                           int64_t bucket_elems);
 /* step 0 clones the gradient into the momentum buffer (sgd.py): tell the model which step it is */
 int b2_model_ddp_first_step(b2_model *m, int first);
 int b2_model_num_buckets(const b2_model *m);
