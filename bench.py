@@ -230,6 +230,7 @@ def run_b2(args):
     launches = b2.lib().b2_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     final_loss = last.item()
+    net.engine.check()
     for _ in range(2):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)

@@ -43,6 +43,7 @@ _SIGS = {
     "b2_model_profile": (_i, [_vp, _i]),
     "b2_model_profile_collect": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i)]),
     "b2_model_time_conv_kernels": (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i), _vp]),
+    "b2_model_check": (_i, [_vp]),
     "b2_model_num_ops": (_i, [_vp]),
     "b2_model_read_activation": (_i, [_vp, _i, _i, _vp, _i64, C.POINTER(_i64), C.POINTER(_i), _vp]),
     "b2_preprocess_u8": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp]),

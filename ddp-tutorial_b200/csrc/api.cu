@@ -161,6 +161,15 @@ int b2_model_time_conv_kernels(b2_model *h, int iters, double *ms3, double *flop
     return h->m->time_conv_kernels(iters, ms3, flops3, launches3, (cudaStream_t)stream);
     GUARD_END
 }
+int b2_model_check(b2_model *h) {
+    GUARD_BEGIN
+    B2_CHECK(h, B2_ERR_ARG, "NULL model");
+    int e = 0;
+    B2_CUDA(cudaMemcpy(&e, h->m->fb_err, sizeof(int), cudaMemcpyDeviceToHost));
+    B2_CHECK(e == 0, B2_ERR_TIMEOUT, "model: a fused conv+BatchNorm grid barrier timed out (grid not co-resident?)");
+    return 0;
+    GUARD_END
+}
 int b2_model_num_ops(const b2_model *h) { return h ? (int)h->m->ops.size() : 0; }
 int b2_model_read_activation(b2_model *h, int op, int want_grad, float *out, int64_t capacity, int64_t *numel,
                              int shape[4], void *stream) {

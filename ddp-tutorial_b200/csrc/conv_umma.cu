@@ -270,9 +270,9 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
                 }
             }
         }
+        const int e = (warp - 2) * 32 + lane;
         if (want_fwd || want_bwd) {
             asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
-            const int e = (warp - 2) * 32 + lane;
             const int c = e & 63, r0 = (e >> 6) * 64;
             float s0 = 0.f, s1 = 0.f;
             if (want_fwd) {
@@ -285,6 +285,68 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
             float *st = (want_fwd ? p.stats : p.bn_bsum) + (size_t)((blockIdx.x + blockIdx.z) % kBnSumCopies) * 2 * p.out_C;
             atomicAdd(st + ch0 + c, s0);
             atomicAdd(st + p.out_C + ch0 + c, s1);
+        }
+        if (p.fuse_bn) {
+            // ---- grid-wide barrier: every CTA of this launch has contributed its tile's sums
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (e == 0) {
+                atomicAdd(p.fb_counter, 1u);
+                const uint32_t total = gridDim.x * gridDim.y * gridDim.z;
+                const long long t0 = clock64();
+                while (ld_acquire_gpu_u32(p.fb_counter) < total)
+                    if (clock64() - t0 > 6000000000LL) { *p.fb_err = 1; break; }      // ~3 s: fail, do not hang
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            float *sS = sT;                                   // [0,64) scale, [64,128) shift of this CTA's channels
+            if (e < 64) {
+                const int c = ch0 + e;
+                float t0s = 0.f, t1s = 0.f;
+#pragma unroll
+                for (int k = 0; k < kBnSumCopies; ++k) { t0s += __ldcg(p.stats + (2 * k) * p.out_C + c); t1s += __ldcg(p.stats + (2 * k + 1) * p.out_C + c); }
+                const double mu = (double)t0s / (double)p.fb_count;
+                double var = (double)t1s / (double)p.fb_count - mu * mu;
+                if (var < 0.0) var = 0.0;
+                const float is = (float)(1.0 / sqrt(var + (double)p.fb_eps));
+                const float g = p.fb_gamma[c];
+                sS[e] = is * g;
+                sS[64 + e] = p.fb_beta[c] - (float)mu * is * g;
+                if (blockIdx.x == 0 && blockIdx.z == 0) {
+                    p.fb_save_mean[c] = (float)mu; p.fb_save_invstd[c] = is;
+                    if (p.fb_running_mean) {
+                        const double unbiased = p.fb_count > 1.f ? var * (double)p.fb_count / ((double)p.fb_count - 1.0) : var;
+                        p.fb_running_mean[c] = (1.f - p.fb_momentum) * p.fb_running_mean[c] + p.fb_momentum * (float)mu;
+                        p.fb_running_var[c] = (1.f - p.fb_momentum) * p.fb_running_var[c] + p.fb_momentum * (float)unbiased;
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            bf16 *ydst = p.fb_y + pix_off;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + half * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int col = half * 32 + j * 8;
+                    uint4 rr = make_uint4(0, 0, 0, 0);
+                    if (p.fb_res) rr = *(const uint4 *)(p.fb_res + pix_off + col);
+                    const __nv_bfloat162 *r2 = (const __nv_bfloat162 *)&rr;
+                    uint4 pk;
+                    __nv_bfloat162 *p2 = (__nv_bfloat162 *)&pk;
+#pragma unroll
+                    for (int k2 = 0; k2 < 4; ++k2) {
+                        // normalise the bf16-rounded conv output (what is stored and what backward reads)
+                        float2 xr = __bfloat1622float2(__floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2 * k2]), __uint_as_float(v[j * 8 + 2 * k2 + 1])));
+                        float a = fmaf(xr.x, sS[col + 2 * k2], sS[64 + col + 2 * k2]);
+                        float b = fmaf(xr.y, sS[col + 2 * k2 + 1], sS[64 + col + 2 * k2 + 1]);
+                        if (p.fb_res) { float2 rf = __bfloat1622float2(r2[k2]); a += rf.x; b += rf.y; }
+                        if (p.fb_relu) { a = a > 0.f ? a : 0.f; b = b > 0.f ? b : 0.f; }
+                        p2[k2] = __floats2bfloat162_rn(a, b);
+                    }
+                    *(uint4 *)(ydst + col) = pk;
+                }
+            }
         }
         }   // !(SPLIT && crank == 1)
         tc_fence_before();

@@ -35,6 +35,17 @@ struct TapGemmParams {
     const bf16 *bn_x, *bn_y;    // the BatchNorm's input / output (same NHWC shape as `out`)
     const float *bn_mean, *bn_invstd;
     int bn_relu;
+    // optional (fprop whose whole grid is co-resident): apply the consumer BatchNorm (+residual, ReLU)
+    // in this kernel.  After a CTA has added its tile's sums to `stats` it joins a grid-wide counter
+    // barrier; the fp32 accumulators stay in TMEM across the barrier and are then normalised and
+    // written as the BatchNorm output `fb_y` (the raw conv output `out` is still stored: backward
+    // needs it).  One launch replaces conv + BN-apply.
+    int fuse_bn;
+    bf16 *fb_y; const bf16 *fb_res;
+    const float *fb_gamma, *fb_beta;
+    float *fb_save_mean, *fb_save_invstd, *fb_running_mean, *fb_running_var;
+    unsigned int *fb_counter; int *fb_err;
+    float fb_count, fb_eps, fb_momentum; int fb_relu;
 };
 
 struct UmmaConvPlan {

@@ -165,9 +165,9 @@ void Model::build_resnet(bool bottleneck, const int layers[4]) {
                 wd = add_conv_weight(pre + ".downsample.0.weight", planes * expansion, inplanes, 1, 1);
                 nd = add_bn_params(*this, pre + ".downsample.1", planes * expansion);
             }
-            // main path first, the downsample branch after it: in backward the block's first conv is
-            // then the LAST writer of the block input's gradient (its dgrad epilogue can finalise
-            // the BatchNorm-backward sums of the tensor it completes)
+            // the block's first conv comes first (in backward it is then the LAST writer of the block
+            // input's gradient); the downsample branch comes before the block's last conv, whose
+            // kernel also applies the final BatchNorm + residual + ReLU
             int idn = t, o;
             auto downsample = [&]() {
                 if (!down) return;
@@ -177,16 +177,16 @@ void Model::build_resnet(bool bottleneck, const int layers[4]) {
             if (!bottleneck) {
                 o = op_conv(t, w1, -1, planes, 3, stride, 1, false, -1);
                 o = op_bn(o, n1.g, n1.b, n1.rm, n1.rv, true, -1);
+                downsample();          // before conv2: conv2's kernel applies bn2 and needs the residual
                 o = op_conv(o, w2, -1, planes, 3, 1, 1, false, -1);
-                downsample();
                 o = op_bn(o, n2.g, n2.b, n2.rm, n2.rv, true, idn);
             } else {
                 o = op_conv(t, w1, -1, planes, 1, 1, 0, false, -1);
                 o = op_bn(o, n1.g, n1.b, n1.rm, n1.rv, true, -1);
                 o = op_conv(o, w2, -1, planes, 3, stride, 1, false, -1);
                 o = op_bn(o, n2.g, n2.b, n2.rm, n2.rv, true, -1);
-                o = op_conv(o, w3, -1, planes * 4, 1, 1, 0, false, -1);
                 downsample();
+                o = op_conv(o, w3, -1, planes * 4, 1, 1, 0, false, -1);
                 o = op_bn(o, n3.g, n3.b, n3.rm, n3.rv, true, idn);
             }
             t = o;
@@ -268,9 +268,10 @@ int Model::finalize() {
         if (o.type != OP_BN) continue;
         for (const Op &c : ops)
             if (c.type == OP_CONV && c.out == o.in && (c.use_umma || c.stem_umma)) o.bn_fused = true;
-        if (o.bn_fused) { sum_off[i] = sums_floats; sums_floats += 4 * (size_t)kBnSumCopies * tensors[o.in].C; }
+        if (o.bn_fused) { sum_off[i] = sums_floats; sums_floats += 4 * (size_t)kBnSumCopies * tensors[o.in].C + 4; }
     }
     size_t sums_off = reserve(sums_floats * 4 + 256);
+    size_t err_off = reserve(256);
     size_t wg_off = reserve(wg_floats * 4 + 256);
     size_t bf_off = precision == B2_PREC_BF16 ? reserve((size_t)n_params * 2 + 256) : 0;
     wgrad_floats = wg_floats;
@@ -292,9 +293,11 @@ int Model::finalize() {
     }
     wgrad_ws = (float *)(base + wg_off);
     bn_sums = (float *)(base + sums_off); bn_sums_bytes = sums_floats * 4;
+    fb_err = (int *)(base + err_off);
     for (size_t i = 0; i < ops.size(); ++i)
         if (ops[i].type == OP_BN && ops[i].bn_fused) {
             ops[i].fsum = bn_sums + sum_off[i]; ops[i].bsum = ops[i].fsum + 2 * (size_t)kBnSumCopies * tensors[ops[i].in].C;
+            ops[i].fb_counter = (unsigned int *)(ops[i].bsum + 2 * (size_t)kBnSumCopies * tensors[ops[i].in].C);
         }
     if (precision == B2_PREC_BF16) { own_bf16 = (bf16 *)(base + bf_off); p_params_bf16 = own_bf16; }
     return 0;
@@ -451,8 +454,29 @@ int Model::build_plans() {
     B2_CUDA(cudaStreamSynchronize(0));
     for (Op &b : ops) {
         if (b.type != OP_BN || !b.bn_fused) continue;
+        b.fwd_in_conv = false;
+        static const bool allow_fb = [] { const char *e = getenv("B2_FUSE_BN_FWD"); return !(e && e[0] == '0'); }();
         for (Op &c : ops)
-            if (c.type == OP_CONV && c.out == b.in) c.fplan.p.stats = b.fsum;
+            if (c.type == OP_CONV && c.out == b.in) {
+                TapGemmParams &q = c.fplan.p;
+                q.stats = b.fsum;
+                const unsigned ctas = c.fplan.grid.x * c.fplan.grid.y * c.fplan.grid.z;
+                // conv + BatchNorm(+residual, ReLU) in one launch when the whole grid is co-resident
+                if (allow_fb && c.use_umma && ctas <= 2u * kNumSMs) {
+                    const Tensor &tx = tensors[b.in];
+                    q.fuse_bn = 1;
+                    q.fb_y = (bf16 *)tensors[b.out].val;
+                    q.fb_res = b.res >= 0 ? (const bf16 *)tensors[b.res].val : nullptr;
+                    q.fb_gamma = p_params + b.w_off; q.fb_beta = p_params + b.b_off;
+                    q.fb_save_mean = b.bn.mean; q.fb_save_invstd = b.bn.invstd;
+                    q.fb_running_mean = p_buffers ? p_buffers + b.rm_off : nullptr;
+                    q.fb_running_var = p_buffers ? p_buffers + b.rv_off : nullptr;
+                    q.fb_counter = b.fb_counter; q.fb_err = fb_err;
+                    q.fb_count = (float)((int64_t)tx.N * tx.H * tx.W); q.fb_eps = 1e-5f; q.fb_momentum = 0.1f;
+                    q.fb_relu = b.relu ? 1 : 0;
+                    b.fwd_in_conv = true;
+                }
+            }
         // last writer of d(b.out) in backward order = its first consumer in forward order
         b.bwd_sums_fused = false;
         for (Op &c : ops) {
@@ -576,6 +600,7 @@ int Model::forward_impl(const float *x_nchw, float *logits, cudaStream_t s) {
         case OP_BN: {
             Tensor &ti = tensors[o.in];
             int64_t M = (int64_t)ti.N * ti.H * ti.W;
+            if (o.bn_fused && o.fwd_in_conv) break;      // done inside the producing conv kernel
             int ph = prof_begin(PC_BN_FWD, 0, ti.numel * (double)dt_size(ti.dt) * (o.res >= 0 ? 4.0 : 3.0), s);
             if (o.bn_fused)
                 B2_TRY(op_bn_forward_fused(ti.val, to.val, o.res >= 0 ? tensors[o.res].val : nullptr, ti.dt, M, ti.C, o.fsum,

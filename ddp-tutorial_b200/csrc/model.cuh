@@ -27,6 +27,8 @@ struct Op {
     BnWork bn;
     bool bn_fused;               // statistics come from the producing conv's epilogue
     float *fsum, *bsum;          // [copies][2][C] each, inside the per-step zeroed arena
+    bool fwd_in_conv;            // forward done inside the producing conv kernel (grid-barrier fusion)
+    unsigned int *fb_counter;
     bool bwd_sums_fused;         // the dgrad that finalises this BN's output gradient also accumulates bsum
     uint8_t *idx;                // maxpool argmax
     int wdt, wpitch;             // conv: weight operand type / row pitch as the kernels see it
@@ -63,6 +65,7 @@ struct Model {
     bf16 *own_bf16 = nullptr;        // model-owned default for the mirror
     void *slab = nullptr; size_t slab_bytes = 0;
     float *wgrad_ws = nullptr; size_t wgrad_floats = 0;
+    int *fb_err = nullptr;           // set by a fused conv+BN kernel whose grid barrier timed out
     float *bn_sums = nullptr; size_t bn_sums_bytes = 0;    // all fused-BN sum buffers, zeroed once per step
     bool weights_dirty = true;
     bool plans_ready = false;

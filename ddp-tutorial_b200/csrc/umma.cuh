@@ -101,6 +101,10 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, f
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t *p) {
+    uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+
 // ---- descriptors ----------------------------------------------------------------------------
 // shared-memory matrix descriptor, 128-byte swizzle (matches CU_TENSOR_MAP_SWIZZLE_128B tiles of
 // [rows][128 B]).  K-major operand: rows = M/N index, 128 B = 64 bf16 along K, SBO = 1024 B

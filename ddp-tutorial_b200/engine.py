@@ -235,6 +235,11 @@ class Engine:
             call("b2_model_set_graphs", m.h, int(enable))
         self._graphs = enable
 
+    def check(self) -> None:
+        """Synchronises; raises if any kernel of this engine's models reported a failure."""
+        for m in self.models.values():
+            call("b2_model_check", m.h)
+
     def steps_tracked(self) -> int:
         return sum(lib().b2_model_steps_tracked(m.h) for m in self.models.values())
 

@@ -113,6 +113,9 @@ int b2_model_profile_collect(b2_model *m, double *ms, double *flops, double *byt
  * [0]=fprop [1]=dgrad [2]=wgrad, with the FLOPs those launches execute.  Clobbers gradients. */
 int b2_model_time_conv_kernels(b2_model *m, int iters, double *ms3, double *flops3, int *launches3,
                                void *stream);
+/* synchronises and reports B2_ERR_TIMEOUT if a fused conv+BatchNorm kernel gave up at its
+ * grid barrier (its results are then invalid) */
+int b2_model_check(b2_model *m);
 /* debugging / parity: copy an internal activation (by op index) out as fp32 NCHW */
 int b2_model_num_ops(const b2_model *m);
 int b2_model_read_activation(b2_model *m, int op, int want_grad, float *out, int64_t capacity,

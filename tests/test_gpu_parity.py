@@ -40,6 +40,7 @@ def run_b2(model, x, y, steps, fixed=True, gen=None, batch=None):
             grads0 = {n: p.grad.detach().cpu().clone() for n, p in model.named_parameters()}
         opt.step()
         losses.append(loss.item())
+    getattr(model, "engine", getattr(getattr(model, "module", None), "engine", None)).check()
     return losses, grads0
 
 
