@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("model,steps,overlap,prec", [("net", 10, "1", "fp32"), ("net", 6, "0", "fp32"),
-                                                      ("resnet18", 6, "1", "fp32"), ("resnet18", 6, "1", "bf16")])
+                                                      ("resnet18", 4, "1", "fp32"), ("resnet18", 6, "1", "bf16")])
 def test_ddp_two_ranks_matches_oracle(model, steps, overlap, prec):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
