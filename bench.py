@@ -276,7 +276,8 @@ def run_b2(args):
                     "flops_counted": "executed (padding-only taps skipped); SURVEY 8d dense count would be "
                                      f"{dense_gflop} GFLOP/step" if dense_gflop else "executed",
                     "how": "each conv launch of the step timed alone: 20 back-to-back launches between two CUDA events "
-                           "(b2_model_time_conv_kernels), summed over the step's launches; per_class = eager per-op "
+                           "(b2_model_time_conv_kernels), summed over the step's launches -- the fprop launches include the "
+                           "BatchNorm apply that is fused into them (no extra FLOPs counted); per_class = eager per-op "
                            "event pass (includes launch gaps)",
                     "kernel_avg": kernel_avg,
                     "share_of_step": conv_ms_eager / total_ms if total_ms else None, "per_class": per}
