@@ -737,7 +737,7 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
             if (o.bn_fused)
                 B2_TRY(op_bn_backward_fused(ti.val, to.val, to.grad, ti.grad, o.res >= 0 ? tensors[o.res].grad : nullptr, ti.dt, M,
                                             ti.C, o.bsum, p_params + o.w_off, p_grads + o.w_off, p_grads + o.b_off, o.relu,
-                                            o.acc_in, o.acc_res, o.bwd_sums_fused, o.bn, s));
+                                            o.acc_in, o.acc_res, o.bwd_sums_fused, o.bn, s, o.fb_counter + 1, fb_err));
             else
             B2_TRY(op_bn_backward(ti.val, to.val, to.grad, ti.grad, o.res >= 0 ? tensors[o.res].grad : nullptr, ti.dt, M,
                                   ti.C, p_params + o.w_off, p_grads + o.w_off, p_grads + o.b_off, o.relu, o.acc_in,
