@@ -240,8 +240,9 @@ int Model::finalize() {
             o.wdt = DT_F32; o.wpitch = o.g.K();
             o.is_fc = tensors[o.in].dt == DT_F32 && tensors[o.out].dt == DT_F32 && o.g.kh == 1 && o.g.Hi == 1 && o.g.Wi == 1 &&
                       o.g.stride == 1 && o.g.pad == 0 && o.g.Co <= 16 && kind != B2_MODEL_NET;
-            if (tensors[o.in].dt == DT_BF16 && o.in == input_tensor && conv_impl == 1 && !o.relu && o.b_off < 0 && o.g.Co % 64 == 0) {
-                o.kpad = (o.g.K() + 63) / 64 * 64;
+            if (tensors[o.in].dt == DT_BF16 && o.in == input_tensor && conv_impl == 1 && !o.relu && o.b_off < 0 && o.g.Co % 64 == 0 &&
+                o.g.kh == 7 && o.g.Ci == 3) {
+                o.kpad = (o.g.Ci * o.g.kh * 8 + 63) / 64 * 64;      // GEMM-K order (c, kh, kw padded to 8)
                 ConvGeom v{};
                 v.N = o.g.N; v.Hi = v.Ho = o.g.Ho; v.Wi = v.Wo = o.g.Wo; v.Ci = o.kpad; v.Co = o.g.Co;
                 v.kh = v.kw = 1; v.stride = 1; v.pad = 0;
@@ -572,7 +573,7 @@ int Model::forward_impl(const float *x_nchw, float *logits, cudaStream_t s) {
             if (o.stem_umma) {
                 int ph = prof_begin(PC_CONV_FPROP, 2.0 * o.g.M() * o.g.Co * o.g.K(), (double)o.vg.M() * o.kpad * 4 + to.numel * 2.0, s);
                 B2_TRY(op_stem_im2col(cur_x, o.col, o.g.N, o.g.Ci, o.g.Hi, o.g.Wi, o.g.kh, o.g.stride, o.g.pad, o.g.Ho, o.g.Wo, o.kpad, s));
-                B2_TRY(op_f32_to_bf16_padded(p_params + o.w_off, o.wpad, o.g.Co, o.g.K(), o.kpad, s));
+                B2_TRY(op_stem_pack_weights(p_params + o.w_off, o.wpad, o.g.Co, o.g.Ci, o.g.kh, o.kpad, s));
                 B2_TRY(umma_conv_launch(o.fplan, s));
                 prof_end(ph, s);
                 break;
@@ -692,7 +693,7 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
                 int ph = prof_begin(PC_CONV_WGRAD, 2.0 * o.g.M() * o.g.Co * o.g.K(), (double)o.vg.M() * o.kpad * 2 + to.numel * 2.0, s);
                 cudaStream_t ws = wgrad_stream();
                 B2_TRY(umma_wgrad_launch(o.wplan, ws));
-                B2_TRY(op_copy_2d_f32(o.dwpad, o.kpad, p_grads + o.w_off, o.g.K(), o.g.Co, o.g.K(), ws));
+                B2_TRY(op_stem_unpack_wgrad(o.dwpad, p_grads + o.w_off, o.g.Co, o.g.Ci, o.g.kh, o.kpad, ws));
                 prof_end(ph, s);
                 break;
             }

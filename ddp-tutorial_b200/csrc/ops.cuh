@@ -65,6 +65,11 @@ int op_maxpool_backward_bf16x8(const bf16 *dy, const uint8_t *idx, bf16 *dx, int
 // column order (kh, kw, c) = the O,H,W,I weight order; columns >= k*k*C are zero
 int op_stem_im2col(const float *x_nchw, bf16 *col, int N, int C, int H, int W, int k, int stride, int pad, int Ho,
                    int Wo, int kpad, cudaStream_t s);
+// The stem's GEMM-K order is (c, kh, kw padded to 8): one 16-byte im2col chunk = 8 consecutive input
+// pixels of one (channel, filter row).  pack: fp32 O,H,W,I master -> bf16 [Co][kpad] in that order;
+// unpack: fp32 dW [Co][kpad] in that order -> O,H,W,I gradient rows.
+int op_stem_pack_weights(const float *master, bf16 *wpad, int Co, int C, int k, int kpad, cudaStream_t s);
+int op_stem_unpack_wgrad(const float *dwpad, float *grad, int Co, int C, int k, int kpad, cudaStream_t s);
 // dst[r][0:cols] = src[r][0:cols] for row pitches dpitch / spitch (fp32)
 int op_copy_2d_f32(const float *src, int spitch, float *dst, int dpitch, int rows, int cols, cudaStream_t s);
 

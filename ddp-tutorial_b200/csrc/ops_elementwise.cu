@@ -604,47 +604,78 @@ int op_maxpool_backward_bf16x8(const bf16 *dy, const uint8_t *idx, bf16 *dx, int
 }
 
 // ---- stem im2col.  One block per image: the whole fp32 image (CH x H x W, 12 KB for CIFAR) is
-// staged in shared memory with coalesced loads, then every thread emits 16-byte chunks of the
-// bf16 im2col rows (column order (kh, kw, c), zero beyond KS*KS*CH).
+// staged in shared memory with coalesced loads, then every thread emits 16-byte chunks of the bf16
+// im2col rows.  GEMM-K order (c, kh, kw8): chunk j < CH*KS is (c = j / KS, kh = j % KS) and holds the
+// 8 consecutive input pixels wi = wo*stride - pad + 0..7 of row hi (the 8th has a zero weight); chunks
+// beyond CH*KS are zero.  No per-element index arithmetic.
 template <int KS, int CH>
 __global__ void __launch_bounds__(256)
 k_stem_im2col(const float *__restrict__ x, bf16 *__restrict__ col, int N, int H, int W, int stride, int pad,
               int Ho, int Wo, int kpad) {
     pdl_sync();
-    extern __shared__ float simg[];                 // [CH][H][W]
+    static_assert(KS <= 8, "one filter row per 8-wide chunk");
+    extern __shared__ float simg[];                 // [CH][H][W + 1]: odd row pitch, lanes on different rows hit different banks
     const int n = blockIdx.x;
-    const float4 *src = (const float4 *)(x + (int64_t)n * CH * H * W);
-    for (int i = threadIdx.x; i < CH * H * W / 4; i += blockDim.x) ((float4 *)simg)[i] = src[i];
+    const int WP = W + 1;
+    const float *src = x + (int64_t)n * CH * H * W;
+    for (int i = threadIdx.x; i < CH * H * W; i += blockDim.x) { const int r = i / W; simg[r * WP + (i - r * W)] = src[i]; }
     __syncthreads();
-    constexpr int K = KS * KS * CH;
     const int chunks = kpad >> 3;
     bf16 *obase = col + (int64_t)n * Ho * Wo * kpad;
     const int items = Ho * Wo * chunks;
     for (int i = threadIdx.x; i < items; i += blockDim.x) {
-        const int ch = i % chunks, pix = i / chunks;
+        const int j = i % chunks, pix = i / chunks;
         const int ho = pix / Wo, wo = pix - ho * Wo;
         __align__(16) bf16 o[8];
+        const int c = j / KS, kh = j - c * KS;
+        const int hi = ho * stride - pad + kh, wi0 = wo * stride - pad;
+        const bool live = j < CH * KS && hi >= 0 && hi < H;
+        const float *row = simg + (c * H + (live ? hi : 0)) * WP;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int kk = ch * 8 + e;
-            float v = 0.f;
-            if (kk < K) {
-                const int tap = kk / CH, c = kk - tap * CH;
-                const int kh = tap / KS, kw = tap - kh * KS;
-                const int hi = ho * stride - pad + kh, wi = wo * stride - pad + kw;
-                if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = simg[(c * H + hi) * W + wi];
-            }
-            o[e] = __float2bfloat16_rn(v);
+            const int wi = wi0 + e;
+            o[e] = __float2bfloat16_rn((live && wi >= 0 && wi < W) ? row[wi] : 0.f);
         }
-        *(uint4 *)(obase + (int64_t)pix * kpad + ch * 8) = *(uint4 *)o;
+        *(uint4 *)(obase + (int64_t)pix * kpad + j * 8) = *(uint4 *)o;
     }
 }
 int op_stem_im2col(const float *x_nchw, bf16 *col, int N, int C, int H, int W, int k, int stride, int pad, int Ho, int Wo,
                    int kpad, cudaStream_t s) {
-    B2_CHECK(kpad % 8 == 0 && kpad >= k * k * C, B2_ERR_ARG, "stem im2col: bad kpad %d", kpad);
+    B2_CHECK(kpad % 8 == 0 && kpad >= C * k * 8, B2_ERR_ARG, "stem im2col: bad kpad %d", kpad);
     B2_CHECK(k == 7 && C == 3 && (C * H * W) % 4 == 0, B2_ERR_UNSUPPORTED, "stem im2col: only the 7x7 / 3-channel ResNet stem is instantiated");
-    size_t smem = (size_t)C * H * W * sizeof(float);
+    size_t smem = (size_t)C * H * (W + 1) * sizeof(float);
     B2_LAUNCH((k_stem_im2col<7, 3>), N, 256, smem, s, x_nchw, col, N, H, W, stride, pad, Ho, Wo, kpad);
+    return 0;
+}
+
+__global__ void k_stem_pack_weights(const float *__restrict__ m, bf16 *__restrict__ w, int Co, int C, int k, int kpad) {
+    pdl_sync();
+    const int total = Co * kpad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int co = i / kpad, kk = i - co * kpad;
+        const int kw = kk & 7, j = kk >> 3;
+        const int c = j / k, kh = j - c * k;
+        float v = 0.f;
+        if (j < C * k && kw < k) v = m[((int64_t)co * k * k + kh * k + kw) * C + c];
+        w[i] = __float2bfloat16_rn(v);
+    }
+}
+int op_stem_pack_weights(const float *master, bf16 *wpad, int Co, int C, int k, int kpad, cudaStream_t s) {
+    B2_LAUNCH(k_stem_pack_weights, (Co * kpad + 255) / 256, 256, 0, s, master, wpad, Co, C, k, kpad);
+    return 0;
+}
+__global__ void k_stem_unpack_wgrad(const float *__restrict__ dwpad, float *__restrict__ g, int Co, int C, int k, int kpad) {
+    pdl_sync();
+    const int K = k * k * C, total = Co * K;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int co = i / K, r = i - co * K;
+        const int c = r % C, tap = r / C;
+        const int kh = tap / k, kw = tap - kh * k;
+        g[i] = dwpad[(int64_t)co * kpad + (c * k + kh) * 8 + kw];
+    }
+}
+int op_stem_unpack_wgrad(const float *dwpad, float *grad, int Co, int C, int k, int kpad, cudaStream_t s) {
+    B2_LAUNCH(k_stem_unpack_wgrad, (Co * k * k * C + 255) / 256, 256, 0, s, dwpad, grad, Co, C, k, kpad);
     return 0;
 }
 
