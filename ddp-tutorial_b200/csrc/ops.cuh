@@ -12,8 +12,6 @@ static inline size_t dt_size(int dt) { return dt == DT_F32 ? 4 : 2; }
 int op_nchw_to_nhwc(const float *x, void *y, int dt, int N, int C, int H, int W, cudaStream_t s);
 int op_nhwc_to_nchw_f32(const void *x, int dt, float *y, int N, int C, int H, int W, cudaStream_t s);
 int op_f32_to_bf16(const float *x, bf16 *y, int64_t n, cudaStream_t s);
-// rows x k fp32 -> rows x kpad bf16 (zero padded)
-int op_f32_to_bf16_padded(const float *x, bf16 *y, int64_t rows, int k, int kpad, cudaStream_t s);
 
 // ---- batch norm (training mode, batch statistics) ---------------------------------
 struct BnWork {           // per-BN-layer scratch, all fp32 device pointers
@@ -70,8 +68,6 @@ int op_stem_im2col(const float *x_nchw, bf16 *col, int N, int C, int H, int W, i
 // unpack: fp32 dW [Co][kpad] in that order -> O,H,W,I gradient rows.
 int op_stem_pack_weights(const float *master, bf16 *wpad, int Co, int C, int k, int kpad, cudaStream_t s);
 int op_stem_unpack_wgrad(const float *dwpad, float *grad, int Co, int C, int k, int kpad, cudaStream_t s);
-// dst[r][0:cols] = src[r][0:cols] for row pitches dpitch / spitch (fp32)
-int op_copy_2d_f32(const float *src, int spitch, float *dst, int dpitch, int rows, int cols, cudaStream_t s);
 
 // ---- small fully-connected head in fp32 (classifier: N <= 32 outputs) ------------------------
 int op_fc_forward(const float *x, const float *w, const float *bias, float *y, int B, int K, int N, bool relu, cudaStream_t s);

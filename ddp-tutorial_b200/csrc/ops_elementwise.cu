@@ -66,19 +66,6 @@ int op_f32_to_bf16(const float *x, bf16 *y, int64_t n, cudaStream_t s) {
     B2_LAUNCH(k_f32_to_bf16, grid_for(n, 256), 256, 0, s, x, y, n);
     return 0;
 }
-__global__ void k_f32_to_bf16_padded(const float *__restrict__ x, bf16 *__restrict__ y, int64_t rows, int k, int kpad) {
-    pdl_sync();
-    int64_t total = rows * kpad;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = i / kpad; int c = i - r * kpad;
-        y[i] = c < k ? __float2bfloat16_rn(x[r * k + c]) : __float2bfloat16_rn(0.f);
-    }
-}
-int op_f32_to_bf16_padded(const float *x, bf16 *y, int64_t rows, int k, int kpad, cudaStream_t s) {
-    B2_LAUNCH(k_f32_to_bf16_padded, grid_for(rows * kpad, 256), 256, 0, s, x, y, rows, k, kpad);
-    return 0;
-}
-
 // ---------------------------------------------------------------------------------
 // BatchNorm.  x is [M][C] (NHWC flattened); per-channel statistics over M rows.
 // Block = 32 channels x 8 row lanes; grid = (C/32, row_blocks).
@@ -676,19 +663,6 @@ __global__ void k_stem_unpack_wgrad(const float *__restrict__ dwpad, float *__re
 }
 int op_stem_unpack_wgrad(const float *dwpad, float *grad, int Co, int C, int k, int kpad, cudaStream_t s) {
     B2_LAUNCH(k_stem_unpack_wgrad, (Co * k * k * C + 255) / 256, 256, 0, s, dwpad, grad, Co, C, k, kpad);
-    return 0;
-}
-
-__global__ void k_copy_2d_f32(const float *__restrict__ src, int spitch, float *__restrict__ dst, int dpitch, int rows, int cols) {
-    pdl_sync();
-    int64_t total = (int64_t)rows * cols;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int c = i % cols; int r = (int)(i / cols);
-        dst[(int64_t)r * dpitch + c] = src[(int64_t)r * spitch + c];
-    }
-}
-int op_copy_2d_f32(const float *src, int spitch, float *dst, int dpitch, int rows, int cols, cudaStream_t s) {
-    B2_LAUNCH(k_copy_2d_f32, grid_for2((int64_t)rows * cols, 256), 256, 0, s, src, spitch, dst, dpitch, rows, cols);
     return 0;
 }
 

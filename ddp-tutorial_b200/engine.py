@@ -97,7 +97,6 @@ class Engine:
         self.flat_buffers: Optional[torch.Tensor] = None
         self.flat_params_bf16: Optional[torch.Tensor] = None   # bf16 mirror shared by all batch sizes
         self.param_views: List[torch.Tensor] = []
-        self._host_init: Optional[Dict[str, torch.Tensor]] = None
         self._last_batch: Optional[int] = None
         self.ddp = None            # set by DistributedDataParallel
         self.optimizer = None      # set by SGD when built from our parameters
