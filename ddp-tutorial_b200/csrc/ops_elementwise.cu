@@ -831,7 +831,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_bn_bwd_reduce_atomic(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy,
                        const float *__restrict__ mean, const float *__restrict__ invstd, bool relu, int64_t M, int C,
-                       int opb /* channel octets per block: min(C/8, 32) */, float *__restrict__ bsum) {
+                       int opb /* channel octets per block: min(C/8, 32) */, float *__restrict__ bsum,
+                       unsigned int *ticket /* zeroed per step; null = no finalize */, const float *__restrict__ gamma,
+                       float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef /* [3][C] */) {
     pdl_sync();
     // each thread owns 8 consecutive channels (16-byte loads); 256/opb row lanes per block
     const int tx = threadIdx.x % opb, ty = threadIdx.x / opb, lanes = 256 / opb;
@@ -875,6 +877,27 @@ k_bn_bwd_reduce_atomic(const T *__restrict__ x, const T *__restrict__ y, const T
             atomicAdd(dst + C + c0 + e, mine[8 + e]);
         }
     }
+    if (ticket) {
+        // the block that finishes last turns the sums into the per-channel coefficients once, so the
+        // apply kernel's blocks read 3 floats per channel instead of re-deriving them from 16 partials
+        __shared__ unsigned int s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1 ? 1u : 0u;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            for (int c = threadIdx.x; c < C; c += blockDim.x) {
+                float sg = 0.f, sgx = 0.f;
+#pragma unroll
+                for (int k = 0; k < kBnSumCopies; ++k) { sg += __ldcg(bsum + (2 * k) * C + c); sgx += __ldcg(bsum + (2 * k + 1) * C + c); }
+                const float isc = invstd[c], muc = mean[c], a = gamma[c] * isc;
+                const float c1 = sg / (float)M, c2 = sgx / (float)M;
+                coef[c] = a; coef[C + c] = -a * c2 * isc; coef[2 * C + c] = -a * c1 + a * c2 * isc * muc;
+                dbeta[c] = sg; dgamma[c] = sgx;
+            }
+        }
+    }
 }
 
 template <typename T, int V>
@@ -882,10 +905,14 @@ __global__ void __launch_bounds__(256)
 k_bn_bwd_apply_fused(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy, T *__restrict__ dx,
                      T *__restrict__ dres, const float *__restrict__ mean, const float *__restrict__ invstd,
                      const float *__restrict__ bsum, const float *__restrict__ gamma, float *__restrict__ dgamma,
-                     float *__restrict__ dbeta, int64_t M, bool relu, bool acc_dx, bool acc_dres, int64_t total, int C) {
+                     float *__restrict__ dbeta, int64_t M, bool relu, bool acc_dx, bool acc_dres, int64_t total, int C,
+                     const float *__restrict__ coef_in /* [3][C] from the reduce kernel, or null */) {
     pdl_sync();
     extern __shared__ float sm[];     // a[C], b[C], k[C]: dx = a*g + b*x + k   (per channel)
     float *ca = sm, *cb = sm + C, *ck = sm + 2 * C;
+    if (coef_in) {
+        for (int c = threadIdx.x; c < 3 * C; c += blockDim.x) sm[c] = coef_in[c];
+    } else
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float sg = 0.f, sgx = 0.f;
 #pragma unroll
@@ -1109,6 +1136,10 @@ int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx,
                          bool acc_dres, bool sums_ready, const BnWork &w, cudaStream_t s, unsigned int *coop_counter,
                          int *coop_err) {
     B2_CHECK(dt == DT_BF16 && C % 8 == 0, B2_ERR_ARG, "bn fused: bf16 activations with C %% 8 == 0 only");
+    bool coef_ready = false;
+    // measured (r01): letting the last reduce block derive the coefficients once is slower (1.019 vs 1.001 ms/step)
+    // than every apply block re-deriving them -- the serial tail costs more than the redundant loads.  Opt-in.
+    static const bool last_block_coef = [] { const char *e = getenv("B2_BN_COEF_LAST"); return e && e[0] == '1'; }();
     // measured (r01): parity-green but 12% slower end to end (1.136 vs 1.011 ms/step): the kernel needs
     // the whole register file of an SM (233-255 regs x 256 threads) and therefore cannot share an SM with
     // the weight-gradient kernels that run concurrently on their own stream.  B2_BN_BWD_COOP=1 enables it.
@@ -1149,13 +1180,14 @@ int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx,
     int64_t maxb = ceil_div(M, (int64_t)lanes * 4); if (want > maxb) want = maxb; if (want < 1) want = 1;
     dim3 grid(gx, (unsigned)want);
     B2_LAUNCH((k_bn_bwd_reduce_atomic<bf16>), grid, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, w.mean, w.invstd,
-              relu, M, C, opb, bsum);
+              relu, M, C, opb, bsum, (coop_counter && last_block_coef) ? coop_counter + 1 : nullptr, gamma, dgamma, dbeta, w.coef);
+    coef_ready = coop_counter != nullptr && last_block_coef;
     }
     int64_t total = M * C;
     int64_t blocks = ceil_div(total / 8, 256); if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
     B2_LAUNCH((k_bn_bwd_apply_fused<bf16, 8>), (int)blocks, 256, 3 * C * sizeof(float), s, (const bf16 *)x, (const bf16 *)y,
               (const bf16 *)dy, (bf16 *)dx, (bf16 *)dres, w.mean, w.invstd, bsum, gamma, dgamma, dbeta, M, relu, acc_dx, acc_dres,
-              total, C);
+              total, C, coef_ready ? (const float *)w.coef : (const float *)nullptr);
     return 0;
 }
 
