@@ -354,3 +354,47 @@ def test_device_prefetcher_delivers_batches_in_order():
     assert len(got) == 7
     for (x, y), (rx, ry) in zip(got, batches):
         assert torch.equal(x, rx) and torch.equal(y, ry)
+
+
+def test_sgd_kernel_bit_identical_to_c_oracle():
+    """b2_sgd against oracle/step_math.c (plain C, no FP contraction): bit-for-bit on p and m,
+    including the bf16 mirror = round-to-nearest-even of the updated fp32 parameter."""
+    import ctypes
+    from oracle import build_c
+    lib = ctypes.CDLL(build_c.build())
+    torch.manual_seed(3)
+    n = 100003
+    p0, grads = torch.randn(n), [torch.randn(n) for _ in range(4)]
+    pc, mc = p0.clone().numpy(), np.zeros(n, dtype=np.float32)
+    pd, md = p0.to(DEV).clone(), torch.zeros(n, device=DEV)
+    npad = (n + 3) // 4 * 4
+    mirror = torch.zeros(npad, dtype=torch.bfloat16, device=DEV)
+    for i, g in enumerate(grads):
+        gn = g.numpy()
+        lib.oracle_sgd_momentum(pc.ctypes.data_as(ctypes.c_void_p), gn.ctypes.data_as(ctypes.c_void_p),
+                                mc.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(n), ctypes.c_float(0.001),
+                                ctypes.c_float(0.9), ctypes.c_int(1 if i == 0 else 0))
+        gd = g.to(DEV)
+        b2._lib.call("b2_sgd", _vp(pd), _vp(gd), _vp(md), n, 0.001, 0.9, 1.0, 1 if i == 0 else 0, _vp(mirror), None)
+    torch.cuda.synchronize()
+    assert np.array_equal(pd.cpu().numpy(), pc)
+    assert np.array_equal(md.cpu().numpy(), mc)
+    assert torch.equal(mirror[:n].cpu(), torch.from_numpy(pc).bfloat16())
+
+
+def test_ce_kernel_against_c_oracle_fp64():
+    import ctypes
+    from oracle import build_c
+    lib = ctypes.CDLL(build_c.build())
+    torch.manual_seed(4)
+    B, K = 512, 10
+    lg, y = (torch.randn(B, K) * 3).contiguous(), torch.randint(0, K, (B,))
+    ref_loss, ref_d = ctypes.c_double(), np.zeros((B, K), dtype=np.float64)
+    lib.oracle_ce_loss_grad(lg.numpy().ctypes.data_as(ctypes.c_void_p), y.numpy().ctypes.data_as(ctypes.c_void_p), B, K,
+                            ctypes.byref(ref_loss), ref_d.ctypes.data_as(ctypes.c_void_p))
+    lgd, yd = lg.to(DEV), y.to(DEV)
+    loss, d = torch.empty(1, device=DEV), torch.empty(B, K, device=DEV)
+    b2._lib.call("b2_ce_loss_grad", _vp(lgd), _vp(yd), B, K, _vp(loss), _vp(d), None)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - ref_loss.value) < 2e-6
+    np.testing.assert_allclose(d.cpu().numpy(), ref_d, rtol=2e-5, atol=2e-9)

@@ -102,3 +102,47 @@ def test_resnet_restatement_vs_golden(golden_dir, name, batch, steps):
         np.testing.assert_allclose(_fp(t), g["init"][n], rtol=1e-6, err_msg=n)
     for n, t in r["grads0"]:
         np.testing.assert_allclose(_fp(t)[1:], g["grad0"][n][1:], rtol=1e-3, err_msg=n)
+
+
+# ---- the plain-C restatement (oracle/step_math.c) against torch, and against the Python oracle ----
+def _cmath():
+    import ctypes
+    from oracle import build_c
+    lib = ctypes.CDLL(build_c.build())
+    return lib, ctypes
+
+
+def test_c_sgd_matches_torch_optimizer_bitwise():
+    lib, C = _cmath()
+    torch.manual_seed(0)
+    n = 10007
+    p0, g1, g2, g3 = (torch.randn(n) for _ in range(4))
+    p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.SGD([p], lr=O.LR, momentum=O.MOMENTUM)
+    pc, mc = p0.clone().numpy(), np.zeros(n, dtype=np.float32)
+    for i, g in enumerate((g1, g2, g3)):
+        p.grad = g.clone(); opt.step()
+        gn = g.numpy()
+        lib.oracle_sgd_momentum(pc.ctypes.data_as(C.c_void_p), gn.ctypes.data_as(C.c_void_p), mc.ctypes.data_as(C.c_void_p),
+                                C.c_int64(n), C.c_float(O.LR), C.c_float(O.MOMENTUM), C.c_int(1 if i == 0 else 0))
+    # torch's CPU kernel may or may not fuse the final multiply-add: at most one rounding apart
+    np.testing.assert_allclose(pc, p.detach().numpy(), rtol=2.4e-7, atol=1e-9)
+    np.testing.assert_array_equal(mc, opt.state[p]["momentum_buffer"].numpy())
+
+
+def test_c_cross_entropy_matches_torch_fp64():
+    lib, C = _cmath()
+    torch.manual_seed(2)
+    B, K = 37, 10
+    lg, y = (torch.randn(B, K) * 4).contiguous(), torch.randint(0, K, (B,))
+    loss, d = C.c_double(), np.zeros((B, K), dtype=np.float64)
+    lib.oracle_ce_loss_grad(lg.numpy().ctypes.data_as(C.c_void_p), y.numpy().ctypes.data_as(C.c_void_p), B, K, C.byref(loss),
+                            d.ctypes.data_as(C.c_void_p))
+    l64 = lg.double().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(l64, y)
+    ref.backward()
+    assert abs(loss.value - float(ref)) < 1e-12
+    np.testing.assert_allclose(d, l64.grad.numpy(), atol=1e-14)
+    l32, d32 = O.cross_entropy_and_grad(lg, y)
+    assert abs(float(l32) - loss.value) < 1e-6
+    np.testing.assert_allclose(d32.numpy(), d, atol=1e-7)
