@@ -72,6 +72,9 @@ _SIGS = {
     "b2_model_set_fused_sgd": (_i, [_vp, _i, _vp, _f, _f, _i64]),
     "b2_model_ddp_first_step": (_i, [_vp, _i]),
     "b2_model_num_buckets": (_i, [_vp]),
+    "b2_model_bucket_plan": (_i, [_vp, _i64, _i, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i)]),
+    "b2_model_workspace_bytes": (_i64, [_vp]),
+    "b2_model_op_info": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "b2_graph_begin": (_i, [_vp]),
     "b2_graph_end": (_i, [_vp, C.POINTER(_vp)]),
     "b2_graph_launch": (_i, [_vp, _vp]),

@@ -144,6 +144,30 @@ int b2_model_ddp_first_step(b2_model *h, int first) {
     return 0;
 }
 int b2_model_num_buckets(const b2_model *h) { return h ? (int)h->m->buckets.size() : 0; }
+int b2_model_bucket_plan(b2_model *h, int64_t bucket_elems, int max_buckets, int64_t *offsets, int64_t *counts, int *after_op) {
+    GUARD_BEGIN
+    B2_CHECK(h && bucket_elems > 0, B2_ERR_ARG, "bucket_plan: bad arguments");
+    std::vector<Model::Bucket> saved = h->m->buckets;
+    h->m->compute_buckets(bucket_elems);
+    const int n = (int)h->m->buckets.size();
+    for (int i = 0; i < n && i < max_buckets; ++i) {
+        if (offsets) offsets[i] = h->m->buckets[i].off;
+        if (counts) counts[i] = h->m->buckets[i].n;
+        if (after_op) after_op[i] = h->m->buckets[i].after_op;
+    }
+    h->m->buckets = saved;
+    return n;
+    GUARD_END
+}
+int64_t b2_model_workspace_bytes(const b2_model *h) { return h ? (int64_t)h->m->slab_bytes : 0; }
+int b2_model_op_info(const b2_model *h, int op, int *type, int geom[11], int flags[4]) {
+    B2_CHECK(h && op >= 0 && op < (int)h->m->ops.size(), B2_ERR_ARG, "op_info: op %d out of range", op);
+    const Op &o = h->m->ops[op];
+    if (type) *type = o.type;
+    if (geom) { const ConvGeom &g = o.g; int v[11] = {g.N, g.Hi, g.Wi, g.Ci, g.Ho, g.Wo, g.Co, g.kh, g.kw, g.stride, g.pad}; for (int i = 0; i < 11; ++i) geom[i] = v[i]; }
+    if (flags) { flags[0] = o.use_umma; flags[1] = o.stem_umma; flags[2] = o.bn_fused; flags[3] = o.is_fc; }
+    return 0;
+}
 int b2_model_profile(b2_model *h, int enable) {
     B2_CHECK(h, B2_ERR_ARG, "NULL model");
     h->m->profiling = enable != 0;

@@ -276,6 +276,8 @@ int Model::finalize() {
     size_t wg_off = reserve(wg_floats * 4 + 256);
     size_t bf_off = precision == B2_PREC_BF16 ? reserve((size_t)n_params * 2 + 256) : 0;
     wgrad_floats = wg_floats;
+    slab_bytes = total;
+    if (device < 0) return 0;        // metadata-only instance (layout / schedule queries on a host without a GPU)
     B2_CUDA(cudaMalloc(&slab, total));
     B2_CUDA(cudaMemset(slab, 0, total));
     slab_bytes = total;
@@ -537,6 +539,7 @@ int Model::run_graphed(std::vector<GraphEntry> &cache, const void *a, const void
 }
 
 int Model::forward(const float *x_nchw, float *logits, cudaStream_t s) {
+    B2_CHECK(device >= 0 && slab, B2_ERR_STATE, "model: metadata-only instance (created with device < 0) cannot execute");
     B2_CHECK(p_params && p_grads, B2_ERR_STATE, "model: parameters/gradients not bound (b2_model_bind)");
     if (!plans_ready) B2_TRY(build_plans());
     // the first two calls run eagerly (lazy module loading, function attributes), then replay
@@ -637,6 +640,7 @@ int Model::forward_impl(const float *x_nchw, float *logits, cudaStream_t s) {
 }
 
 int Model::backward(const float *dlogits, cudaStream_t s) {
+    B2_CHECK(device >= 0 && slab, B2_ERR_STATE, "model: metadata-only instance (created with device < 0) cannot execute");
     B2_CHECK(p_params && p_grads, B2_ERR_STATE, "model: parameters/gradients not bound (b2_model_bind)");
     if (use_graphs && !profiling && eager_runs_bwd >= 2) return run_graphed(bwd_graphs, dlogits, nullptr, false, s);
     ++eager_runs_bwd;
@@ -777,7 +781,7 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
 int Model::create(int kind, int batch, int num_classes, int precision, int device, Model **out) {
     B2_CHECK(batch > 0 && num_classes > 0, B2_ERR_ARG, "model: batch and num_classes must be positive");
     B2_CHECK(precision == B2_PREC_FP32 || precision == B2_PREC_BF16, B2_ERR_ARG, "model: unknown precision %d", precision);
-    B2_CUDA(cudaSetDevice(device));
+    if (device >= 0) B2_CUDA(cudaSetDevice(device));
     Model *m = new Model();
     m->kind = kind; m->batch = batch; m->num_classes = num_classes; m->precision = precision; m->device = device;
     if (kind == B2_MODEL_NET) { m->precision = B2_PREC_FP32; m->build_net(); }

@@ -201,6 +201,17 @@ int b2_model_set_fused_sgd(b2_model *m, int enable, float *momentum_buf, float l
 /* step 0 clones the gradient into the momentum buffer (sgd.py): tell the model which step it is */
 int b2_model_ddp_first_step(b2_model *m, int first);
 int b2_model_num_buckets(const b2_model *m);
+/* the gradient-bucket schedule for a given bucket size, without enabling anything (returns the
+ * number of buckets; arrays receive up to max_buckets entries: element offset, element count, index
+ * of the op whose backward completes the bucket).  Works on metadata-only models. */
+int b2_model_bucket_plan(b2_model *m, int64_t bucket_elems, int max_buckets, int64_t *offsets,
+                         int64_t *counts, int *after_op);
+/* b2_model_create with device < 0 builds a metadata-only instance (no CUDA call): parameter table,
+ * op list and schedules can be queried on a host without a GPU; forward/backward return an error. */
+int64_t b2_model_workspace_bytes(const b2_model *m);
+/* op i of the static graph: type (0 input, 1 conv/linear, 2 batchnorm, 3 maxpool, 4 avgpool),
+ * geom = {N,Hi,Wi,Ci,Ho,Wo,Co,kh,kw,stride,pad}, flags = {tcgen05 conv, tcgen05 stem, fused BN, fc head} */
+int b2_model_op_info(const b2_model *m, int op, int *type, int geom[11], int flags[4]);
 
 /* ---- CUDA-graph capture of a step (launch-latency removal) ---------------- */
 int b2_graph_begin(void *stream);

@@ -1,5 +1,6 @@
 """CPU: host-side logic and the C-ABI library surface (no compute without a GPU)."""
 import ctypes
+import numpy as np
 import os
 import re
 import types
@@ -120,3 +121,101 @@ def test_distributed_sampler_matches_torch(n, world, shuffle, drop_last):
             ref.set_epoch(epoch); mine.set_epoch(epoch)
             assert list(ref) == list(mine)
             assert len(ref) == len(mine)
+
+
+# ---- metadata-only model instances (device < 0): layout and schedules without a GPU ------------------
+def _dry_model(kind, batch, prec):
+    h = ctypes.c_void_p()
+    _lib.call("b2_model_create", {"net": 0, "resnet18": 1, "resnet50": 2}[kind], batch, 10, {"fp32": 0, "bf16": 1}[prec], -1,
+              ctypes.byref(h))
+    return h
+
+
+def _param_table(h):
+    l = b2.lib()
+    out = []
+    for i in range(l.b2_model_num_tensors(h)):
+        name, off, rank = ctypes.c_char_p(), ctypes.c_int64(), ctypes.c_int()
+        shape, stride = (ctypes.c_int64 * 4)(), (ctypes.c_int64 * 4)()
+        _lib.call("b2_model_tensor_info", h, i, ctypes.byref(name), ctypes.byref(off), ctypes.byref(rank), shape, stride)
+        out.append((name.value.decode(), off.value, tuple(shape[:rank.value]), tuple(stride[:rank.value])))
+    return out
+
+
+@pytest.mark.parametrize("kind", ["resnet18", "resnet50"])
+def test_param_table_matches_torchvision(kind):
+    tv = pytest.importorskip("torchvision")
+    ref = getattr(tv.models, kind)(num_classes=10)
+    h = _dry_model(kind, 64, "bf16")
+    table = _param_table(h)
+    assert [(n, tuple(p.shape)) for n, p in ref.named_parameters()] == [(n, s) for n, _, s, _ in table]
+    # flat layout: ascending, 64-element aligned, non-overlapping; conv weights are O,H,W,I strided views
+    end = 0
+    for name, off, shape, stride in table:
+        assert off % 64 == 0 and off >= end
+        numel = int(np.prod(shape))
+        end = off + numel
+        if len(shape) == 4:
+            O, I, H, W = shape
+            assert stride == (H * W * I, 1, W * I, I), name
+    assert end <= b2.lib().b2_model_param_count(h)
+    # buffers: running_mean / running_var of every BatchNorm, torch names
+    names = []
+    for i in range(b2.lib().b2_model_num_buffers(h)):
+        nm, off, n = ctypes.c_char_p(), ctypes.c_int64(), ctypes.c_int64()
+        _lib.call("b2_model_buffer_info", h, i, ctypes.byref(nm), ctypes.byref(off), ctypes.byref(n))
+        names.append(nm.value.decode())
+    assert names == [n for n, _ in ref.named_buffers() if not n.endswith("num_batches_tracked")]
+    # a metadata-only instance refuses to execute
+    assert b2.lib().b2_forward(h, ctypes.c_void_p(8), None, None) != 0
+    b2.lib().b2_model_destroy(h)
+
+
+def test_net_param_table_and_flatten_order():
+    h = _dry_model("net", 4, "fp32")
+    table = _param_table(h)
+    assert [n for n, *_ in table] == ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "fc1.weight", "fc1.bias",
+                                      "fc2.weight", "fc2.bias", "fc3.weight", "fc3.bias"]
+    assert dict((n, s) for n, _, s, _ in table)["fc1.weight"] == (120, 400)
+    b2.lib().b2_model_destroy(h)
+
+
+@pytest.mark.parametrize("kind,bucket", [("resnet18", 2 << 20), ("resnet18", 8 << 20), ("resnet50", 2 << 20), ("net", 4096)])
+def test_bucket_plan_partitions_the_flat_vector(kind, bucket):
+    """DDP buckets (reducer.hpp:30-31 analogue): contiguous suffixes of the flat gradient vector in the
+    order backward completes them; together they cover [0, n) exactly once."""
+    h = _dry_model(kind, 64, "bf16" if kind != "net" else "fp32")
+    n = b2.lib().b2_model_param_count(h)
+    offs, cnts, after = (ctypes.c_int64 * 64)(), (ctypes.c_int64 * 64)(), (ctypes.c_int * 64)()
+    nb = b2.lib().b2_model_bucket_plan(h, bucket, 64, offs, cnts, after)
+    assert 1 <= nb <= 64
+    ivals = sorted((offs[i], offs[i] + cnts[i]) for i in range(nb))
+    assert ivals[0][0] == 0 and ivals[-1][1] == n
+    for (a0, a1), (b0, b1) in zip(ivals, ivals[1:]):
+        assert a1 == b0
+    # produced in descending-offset order, by ops in descending index order (backward order)
+    assert [offs[i] for i in range(nb)] == sorted([offs[i] for i in range(nb)], reverse=True)
+    assert [after[i] for i in range(nb)] == sorted([after[i] for i in range(nb)], reverse=True)
+    # every bucket but the last one is at least the requested size
+    assert all(cnts[i] >= bucket for i in range(nb - 1))
+    b2.lib().b2_model_destroy(h)
+
+
+def test_op_schedule_and_kernel_selection():
+    """Static graph of ResNet-18 at the benchmark shape: 21 conv/linear ops, 20 BatchNorms; in bf16 mode
+    every 64-multiple conv runs on the tcgen05 path, the 3-channel stem on the im2col+tcgen05 path, the
+    classifier on the fp32 head kernels; in fp32 mode nothing does."""
+    for prec, expect_umma in (("bf16", 19), ("fp32", 0)):
+        h = _dry_model("resnet18", 512, prec)
+        nops = b2.lib().b2_model_num_ops(h)
+        types, umma, stem, fused, fc = [], 0, 0, 0, 0
+        for i in range(nops):
+            t, geom, flags = ctypes.c_int(), (ctypes.c_int * 11)(), (ctypes.c_int * 4)()
+            _lib.call("b2_model_op_info", h, i, ctypes.byref(t), geom, flags)
+            types.append(t.value)
+            umma += flags[0]; stem += flags[1]; fused += flags[2]; fc += flags[3]
+        assert types.count(1) == 21 and types.count(2) == 20 and types.count(3) == 1 and types.count(4) == 1
+        assert umma == expect_umma and stem == (1 if prec == "bf16" else 0) and fc == 1
+        assert fused == (20 if prec == "bf16" else 0)
+        assert b2.lib().b2_model_workspace_bytes(h) > 0
+        b2.lib().b2_model_destroy(h)
