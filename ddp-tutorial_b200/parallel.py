@@ -21,6 +21,7 @@ from ._lib import B2Error, call, lib
 from .engine import _stream_ptr
 
 _state = {"rank": 0, "world": 1, "gpu": 0, "distributed": False, "comm": False, "pg": False}
+_wrappers: List["DistributedDataParallel"] = []      # live wrappers (their peer mappings are closed in destroy())
 
 
 def init_distributed(args) -> None:
@@ -163,8 +164,15 @@ class DistributedDataParallel:
         _exchange("params-copied")
         e.mark_weights_dirty()
         e.ddp = self
+        _wrappers.append(self)
         if e.optimizer is not None:
             self._attach_optimizer(e.optimizer)
+
+    def _close_peers(self):
+        """Unmap the peers' buffers (cudaIpcCloseMemHandle).  The model must not be used afterwards."""
+        for ptr in self._peer_ptrs:
+            lib().b2_comm_unimport(C.c_void_p(ptr))
+        self._peer_ptrs = []
 
     def _attach_optimizer(self, opt):
         """Called when an SGD is built over this model's parameters (cifar_example_ddp.py:86)."""
@@ -243,7 +251,14 @@ def check() -> None:
 def destroy() -> None:
     if _state["comm"]:
         torch.cuda.synchronize()
-        call("b2_comm_finalize")
+        if _state["pg"]:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.barrier()                 # nobody unmaps while a peer may still be inside a comm kernel
+        for w in _wrappers:
+            w._close_peers()
+        _wrappers.clear()
+        call("b2_comm_finalize")               # frees this rank's buffers: wrapped models are dead after this
         _state["comm"] = False
     if _state["pg"]:
         import torch.distributed as dist
