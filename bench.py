@@ -270,8 +270,9 @@ def run_b2(args):
             pass
         dense_gflop = TRAIN_FLOP_PER_IMG * BATCH / 1e9 if MODEL == "resnet18" else None
         roofline = {"bound": "tensor", "kernel": "conv implicit-GEMM kernels (k_tapgemm fprop+dgrad, k_wgrad) of one step",
-                    "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
-                    "peak_source": f"{src} (cuBLAS bf16 sustained)", "traffic": traffic,
+                    "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
+                    "peak_source": f"{src} MEASURED_PEAKS bf16_tflops (burst: the conv launches are timed alone)",
+                    "frac_of_sustained_peak": achieved / tf_sus, "traffic": traffic,
                     "traffic_note": "dram bytes of ONE layer1 k_tapgemm launch (profiles/r01_traffic.json); algorithmic 8.45 MB",
                     "flops_counted": "executed (padding-only taps skipped); SURVEY 8d dense count would be "
                                      f"{dense_gflop} GFLOP/step" if dense_gflop else "executed",
