@@ -27,7 +27,6 @@ sys.path.insert(0, ROOT)
 
 MODEL = "resnet18"
 BATCH = 512                      # per GPU (BASELINE configs[1], configs[2])
-TRAIN_FLOP_PER_IMG = 217.28e6    # dense implicit-GEMM count, fprop+dgrad+wgrad
 METRIC = "images/sec (device-timed, max over ranks) ResNet-18 CIFAR-shape"
 
 
@@ -145,32 +144,85 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------
 # this repo's arm
 # ----------------------------------------------------------------------------------------
-def run_b2(args):
+TRAIN_FLOP = {"resnet18": 217.28e6, "resnet50": 495.77e6}      # SURVEY.md 8(d), dense count per image
+
+
+def ddp_parity(b2, O, ns, model_name, batch, precision, dev, rank, world, overlap, bucket_mb):
+    """Multi-GPU parity on the benchmarked model, run before timing (the driver's SCALE runs see it):
+    rank-0 init wins (ranks are seeded differently, cifar_example_ddp.py:83 -> distributed.py:883-890),
+    replicas stay bit-identical, rank 0's loss and the parameter update follow the oracle's world=N run."""
     import torch
-    import ddp_tutorial_b200 as b2
+    import torch.distributed as dist
+    steps = 2
+    torch.manual_seed(0 if rank == 0 else 1234 + rank)
+    net = getattr(b2, model_name)(num_classes=10, precision=precision).to(dev)
+    model = b2.DistributedDataParallel(net, device_ids=[dev], overlap=overlap, bucket_cap_mb=bucket_mb)
+    crit = b2.CrossEntropyLoss()
+    opt = b2.SGD(model.parameters(), lr=0.001, momentum=0.9)
+    e = net.engine
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
-    ns = argparse.Namespace()
-    import contextlib
-    with contextlib.redirect_stdout(sys.stderr):      # keep stdout to the one JSON line
-        b2.init_distributed(ns)
-    dev = ns.gpu
-    torch.cuda.set_device(dev)
+    def replicas_identical():
+        flat = e.flat_params[:e.n_params].cpu()
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        same = torch.tensor([1 if torch.equal(flat, ref) else 0])
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        return bool(same.item())
 
-    torch.manual_seed(0)
-    net = getattr(b2, MODEL)(num_classes=10, precision=args.precision).to(dev)
+    init_same = replicas_identical()
+    p0 = e.flat_params[:e.n_params].cpu().clone()
+    r = O.train(model_name, seed=0, batch=batch, steps=steps, world=world) if rank == 0 else None
+    xg, yg = O.synthetic_batch(O.data_generator(0), batch * world)
+    x, y = xg[rank * batch:(rank + 1) * batch].to(dev), yg[rank * batch:(rank + 1) * batch].to(dev)
+    losses = []
+    for _ in range(steps):
+        opt.zero_grad()
+        loss = crit(model(x), y)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    torch.cuda.synchronize()
+    b2.check(net)
+    same = replicas_identical()
+    out = {"replicas_identical_after_init": init_same, "replicas_identical_after_steps": same, "steps": steps}
+    ok = init_same and same
+    if rank == 0:
+        names = {s.name: s for s in e.specs}
+        upd, ref_upd = [], []
+        init = dict(r["init"])
+        for n, t in r["final"]:
+            s_ = names[n]
+            mine = torch.as_strided(e.flat_params.cpu(), s_.shape, s_.stride, s_.offset) - torch.as_strided(p0, s_.shape, s_.stride, s_.offset)
+            upd.append(mine.flatten().double()); ref_upd.append((t - init[n]).flatten().double())
+        upd, ref_upd = torch.cat(upd), torch.cat(ref_upd)
+        out["loss"] = losses
+        out["loss_err"] = [abs(a - b) for a, b in zip(losses, r["loss"])]
+        out["update_rel_err"] = float((upd - ref_upd).norm() / ref_upd.norm())
+        out["update_cos"] = float((upd @ ref_upd) / (upd.norm() * ref_upd.norm()))
+        tol = 1e-3 if precision == "fp32" else (2e-2 if model_name == "resnet18" else 1e-1)
+        out["loss_tol"] = tol
+        ok = ok and max(out["loss_err"]) < tol and out["update_cos"] > (0.999 if precision == "fp32" else 0.85)
+    flag = torch.tensor([1 if ok else 0])
+    dist.broadcast(flag, 0)
+    out["ok"] = bool(flag.item())
+    del opt, model, net
+    return out
+
+
+def measure(b2, args, ns, model_name, batch, dev, rank, full):
+    """Build `model_name` at per-GPU `batch`, time K steps resident + K steps end-to-end; `full` adds the
+    roofline leg and the clock sampler."""
+    import torch
+    torch.manual_seed(0 if rank == 0 else 1234 + rank)        # rank 0's init wins under DDP
+    net = getattr(b2, model_name)(num_classes=10, precision=args.precision).to(dev)
     model = (b2.DistributedDataParallel(net, device_ids=[dev], overlap=not args.no_overlap, bucket_cap_mb=args.bucket_mb)
              if ns.distributed else net)
     criterion = b2.CrossEntropyLoss()
     optimizer = b2.SGD(model.parameters(), lr=0.001, momentum=0.9)
 
     gen = torch.Generator().manual_seed(1 + rank)
-    x_host = torch.randn(BATCH, 3, 32, 32, generator=gen).pin_memory()
-    y_host = torch.randint(0, 10, (BATCH,), generator=gen).pin_memory()
+    x_host = torch.randn(batch, 3, 32, 32, generator=gen).pin_memory()
+    y_host = torch.randint(0, 10, (batch,), generator=gen).pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
     def step_resident():
@@ -219,27 +271,30 @@ def run_b2(args):
         sync_all()
         return ms, last
 
-    sampler = ClockSampler(dev) if (rank == 0 and not args.no_clocks) else None   # nvidia-smi needs ~1 s to start
-    for _ in range(max(args.warmup, 3)):
+    sampler = ClockSampler(dev) if (full and rank == 0 and not args.no_clocks) else None   # nvidia-smi needs ~1 s to start
+    untimed = max(args.warmup, 3)
+    for _ in range(untimed):
         step_resident()
-    if not args.no_clocks:
+    if full and not args.no_clocks:
         for _ in range(800):                                 # ~1 s under load on EVERY rank (same collective count)
             step_resident()                                  # so that nvidia-smi samples flow before the timed region
+        untimed += 800
     launches0 = b2.lib().b2_launch_count()
     ms, last = timed(step_resident, args.steps)
     launches = b2.lib().b2_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     final_loss = last.item()
-    net.engine.check()
+    b2.check(net)
     for _ in range(2):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
+    res = {"ms": ms, "ms_e2e": ms_e2e, "launches": int(launches), "clocks": clocks, "final_loss": final_loss,
+           "untimed_steps": untimed, "h2d": x_host.numel() * 4 + y_host.numel() * 8, "roofline": None}
 
     # ---- roofline leg: events around every op of the dominant kernel class (separate pass)
-    roofline = None
-    if True:                                                 # every rank runs the same steps (collectives must match)
+    if full:                                                 # every rank runs the same steps (collectives must match)
         e = net.engine
-        m = e._model(BATCH)
+        m = e._model(batch)
         b2._lib.call("b2_model_profile", m.h, 1)
         nprof = 3
         for _ in range(nprof):
@@ -261,30 +316,77 @@ def run_b2(args):
         achieved = conv_fl / conv_ms if conv_ms > 0 else 0.0          # GFLOP/ms == TFLOP/s
         kernel_avg = {n: {"ms_per_step": kms[i], "gflop_per_step": kfl[i] / 1e9, "launches": kln[i],
                           "tflops": (kfl[i] / 1e9 / kms[i]) if kms[i] > 0 else 0.0} for i, n in enumerate(("fprop", "dgrad", "wgrad"))}
-        traffic = None
+        traffic, traffic_note = None, None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
                 tj = json.load(f)
-            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic = tj["conv_dram_bytes_per_launch"]
+            traffic_note = tj.get("note")
         except Exception:
             pass
-        dense_gflop = TRAIN_FLOP_PER_IMG * BATCH / 1e9 if MODEL == "resnet18" else None
-        roofline = {"bound": "tensor", "kernel": "conv implicit-GEMM kernels (k_tapgemm fprop+dgrad, k_wgrad) of one step",
-                    "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
-                    "peak_source": f"{src} MEASURED_PEAKS bf16_tflops (burst: the conv launches are timed alone)",
-                    "frac_of_sustained_peak": achieved / tf_sus, "traffic": traffic,
-                    "traffic_note": "dram bytes of ONE layer1 k_tapgemm launch (profiles/r01_traffic.json); algorithmic 8.45 MB",
-                    "flops_counted": "executed (padding-only taps skipped); SURVEY 8d dense count would be "
-                                     f"{dense_gflop} GFLOP/step" if dense_gflop else "executed",
-                    "how": "each conv launch of the step timed alone: 20 back-to-back launches between two CUDA events "
-                           "(b2_model_time_conv_kernels), summed over the step's launches -- the fprop launches include the "
-                           "BatchNorm apply that is fused into them (no extra FLOPs counted); per_class = eager per-op "
-                           "event pass (includes launch gaps)",
-                    "kernel_avg": kernel_avg,
-                    "share_of_step": conv_ms_eager / total_ms if total_ms else None, "per_class": per}
+        dense_gflop = TRAIN_FLOP[model_name] * batch / 1e9
+        res["roofline"] = {
+            "bound": "tensor", "kernel": "conv implicit-GEMM kernels (fprop+dgrad incl. the fused BatchNorm work, wgrad) of one step",
+            "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
+            "peak_source": f"{src} MEASURED_PEAKS bf16_tflops (burst: the conv launches are timed alone)",
+            "frac_of_sustained_peak": achieved / tf_sus, "traffic": traffic, "traffic_note": traffic_note,
+            "flops_counted": f"executed (padding-only taps skipped); SURVEY 8d dense count would be {dense_gflop:.2f} GFLOP/step",
+            "whole_step_tflops_dense_count": dense_gflop / (ms / args.steps),
+            "how": "each conv launch of the step timed alone: 20 back-to-back launches between two CUDA events "
+                   "(b2_model_time_conv_kernels; BatchNorm sum buffers and barrier counters are reset before every launch, so the "
+                   "grid barrier of the fused conv+BN kernels is paid in full), summed over the step's launches; per_class = eager "
+                   "per-op event pass (includes launch gaps)",
+            "kernel_avg": kernel_avg,
+            "share_of_step": conv_ms_eager / total_ms if total_ms else None, "per_class": per}
+    del optimizer, model
+    return res, net
+
+
+def run_b2(args):
+    import torch
+    import ddp_tutorial_b200 as b2
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
+    ns = argparse.Namespace()
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):      # keep stdout to the one JSON line
+        b2.init_distributed(ns)
+    dev = ns.gpu
+    torch.cuda.set_device(dev)
+
+    parity = None
+    if ns.distributed and not args.no_parity:
+        from oracle import ref_step as O               # checker only (the timed region never touches it)
+        parity = ddp_parity(b2, O, ns, MODEL, BATCH, args.precision, dev, rank, world, not args.no_overlap, args.bucket_mb)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "ddp parity check failed", "ddp_parity": parity}), flush=True)
+            b2.destroy()
+            raise SystemExit(3)
+
+    main_res, net = measure(b2, args, ns, MODEL, BATCH, dev, rank, full=True)
+    del net
+    secondary = None
+    if MODEL == "resnet18" and not args.no_secondary:
+        # BASELINE configs[3]: ResNet-50, per-GPU batch 256, same N, shorter run (no roofline leg)
+        sec, net2 = measure(b2, args, ns, "resnet50", 256, dev, rank, full=False)
+        del net2
+        secondary = {"metric": METRIC.replace("ResNet-18", "ResNet-50"), "value": args.gpus * 256 * args.steps / (sec["ms"] / 1e3),
+                     "unit": "images/sec", "ms_per_step": sec["ms"] / args.steps,
+                     "e2e": {"value": args.gpus * 256 * args.steps / (sec["ms_e2e"] / 1e3), "unit": "images/sec",
+                             "ms_per_step": sec["ms_e2e"] / args.steps, "h2d_bytes_per_step": sec["h2d"], "d2h_bytes_per_step": 4},
+                     "gpu_launches": sec["launches"], "final_loss": sec["final_loss"],
+                     "config": {"workload": "resnet50(num_classes=10) training step, per-GPU batch 256, 3x32x32 synthetic (BASELINE configs[3])",
+                                "global_batch": args.gpus * 256, "parallelism": f"dp{args.gpus}"},
+                     "whole_step_tflops_dense_count": TRAIN_FLOP["resnet50"] * 256 / 1e9 / (sec["ms"] / args.steps)}
 
     if rank == 0:
         n = args.gpus
+        ms, ms_e2e = main_res["ms"], main_res["ms_e2e"]
         ips = n * BATCH * args.steps / (ms / 1e3)
         ips_e2e = n * BATCH * args.steps / (ms_e2e / 1e3)
         cpu = None
@@ -294,7 +396,7 @@ def run_b2(args):
                    "sample": "cifar_example.py loop via oracle/ref_step.py, resnet18 batch 128, 12 steps after 3 warm-up"}
         line = {
             "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": n, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "warmup": main_res["untimed_steps"], "warmup_requested": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": f"{MODEL}(num_classes=10) training step, per-GPU batch {BATCH}, 3x32x32 synthetic "
@@ -304,11 +406,13 @@ def run_b2(args):
                        if args.precision == "bf16" else "fp32",
                        "l2": "no explicit flush: one step streams >600 MB of activations/gradients/params, "
                              "several times the 126 MB L2"},
-            "final_loss": final_loss,
+            "final_loss": main_res["final_loss"], "final_loss_after_steps": main_res["untimed_steps"] + args.steps,
             "e2e": {"value": ips_e2e, "unit": "images/sec", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+                    "h2d_bytes_per_step": main_res["h2d"], "d2h_bytes_per_step": 4},
+            "gpu_launches": main_res["launches"],
+            "roofline": main_res["roofline"], "cpu_baseline": cpu, "clocks": main_res["clocks"],
+            "ddp_parity": parity, "secondary": secondary,
+            "env_toggles": {k: v for k, v in sorted(os.environ.items()) if k.startswith("B2_")},
         }
         print(json.dumps(line), flush=True)
     if ns.distributed:
@@ -330,6 +434,8 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="DDP: one fused exchange at optimizer.step() instead of bucketed overlap")
     ap.add_argument("--bucket-mb", type=float, default=32.0)
     ap.add_argument("--no-clocks", action="store_true", help="skip the nvidia-smi sampler (profiler runs)")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the DDP parity phase that runs before timing")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the ResNet-50 (BASELINE configs[3]) secondary measurement")
     args = ap.parse_args()
     MODEL = args.model
     BATCH = args.batch or (512 if MODEL == "resnet18" else 256)

@@ -9,10 +9,10 @@
     optimizer.zero_grad(); loss = criterion(net(x), y); loss.backward(); optimizer.step(); loss.item()
 """
 from ._lib import B2Error, LIB_PATH, lib  # noqa: F401
-from .nn import CrossEntropyLoss, Loss, Module, Net, ResNet, resnet18, resnet50  # noqa: F401
+from .nn import CrossEntropyLoss, Loss, Module, Net, ResNet, RunningLoss, resnet18, resnet50  # noqa: F401
 from .data import Accuracy, DeviceCifarLoader, DevicePrefetcher, DistributedSampler, normalize_u8  # noqa: F401
 from .optim import SGD  # noqa: F401
-from .parallel import DistributedDataParallel, barrier, destroy, init_distributed  # noqa: F401
+from .parallel import DistributedDataParallel, barrier, check, destroy, init_distributed  # noqa: F401
 
-__all__ = ["Accuracy", "DeviceCifarLoader", "DevicePrefetcher", "DistributedSampler", "normalize_u8", "B2Error", "CrossEntropyLoss", "DistributedDataParallel", "Net", "ResNet", "SGD", "barrier",
+__all__ = ["Accuracy", "DeviceCifarLoader", "DevicePrefetcher", "DistributedSampler", "normalize_u8", "B2Error", "CrossEntropyLoss", "DistributedDataParallel", "Net", "ResNet", "RunningLoss", "SGD", "barrier", "check",
            "destroy", "init_distributed", "lib", "resnet18", "resnet50"]

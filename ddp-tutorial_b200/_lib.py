@@ -50,6 +50,7 @@ _SIGS = {
     "b2_argmax_count": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "b2_conv_test": (_i, [_i] * 11 + [_vp, _vp, _vp, _vp, _vp]),
     "b2_ce_loss_grad": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "b2_ce_loss_grad_running": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "b2_sgd": (_i, [_vp, _vp, _vp, _i64, _f, _f, _f, _i, _vp, _vp]),
     "b2_model_bind_bf16": (_i, [_vp, _vp]),
     "b2_model_mark_weights_clean": (_i, [_vp]),

@@ -50,7 +50,8 @@ def main(args):
         net = getattr(b2, args.model)(num_classes=10, precision=args.precision).to(args.gpu)
     if args.distributed:
         net = b2.DistributedDataParallel(net, device_ids=[args.gpu])          # :83
-    criterion = b2.CrossEntropyLoss()                                         # :85
+    running = b2.RunningLoss(args.gpu)                                        # :110 running_loss, kept on the device
+    criterion = b2.CrossEntropyLoss(running=running)                          # :85
     optimizer = b2.SGD(net.parameters(), lr=0.001, momentum=0.9)              # :86
 
     gen = torch.Generator().manual_seed(args.seed + 1 + rank)
@@ -68,7 +69,7 @@ def main(args):
             yield x.to(args.gpu, non_blocking=True), y.to(args.gpu, non_blocking=True)          # :97-98
 
     for epoch in range(args.epochs):                                          # :90
-        running_loss = 0.0
+        running.mean_and_reset()
         if train is not None:
             sampler_train.set_epoch(epoch)                                    # :92
         for i, (inputs, labels) in enumerate(trainloader if train is not None else synthetic()):   # :94
@@ -77,10 +78,10 @@ def main(args):
             loss = criterion(outputs, labels)                                 # :105
             loss.backward()                                                   # :106
             optimizer.step()                                                  # :107
-            running_loss += loss.item()                                       # :110
+            # :110 `running_loss += loss.item()` happens inside the criterion kernel (no host sync per step)
             if i % args.print_every == args.print_every - 1:                  # :111-114
-                print('[%d, %5d] loss: %.3f' % (epoch + 1, i + 1, running_loss / args.print_every))
-                running_loss = 0.0
+                print('[%d, %5d] loss: %.3f' % (epoch + 1, i + 1, running.mean_and_reset()))
+                b2.check(net)                                                 # surfaces a timed-out barrier / peer wait
     print('Finished Training')
     if rank == 0 and args.save:
         torch.save(net.state_dict(), args.save)                               # :118-119 (single writer)

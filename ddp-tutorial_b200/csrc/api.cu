@@ -219,7 +219,14 @@ int b2_ce_loss_grad(const float *logits, const int64_t *labels, int batch, int c
                     void *stream) {
     GUARD_BEGIN
     B2_CHECK(logits && labels && loss_out, B2_ERR_ARG, "b2_ce_loss_grad: NULL argument");
-    return op_ce_loss_grad(logits, labels, batch, classes, loss_out, dlogits, (cudaStream_t)stream);
+    return op_ce_loss_grad(logits, labels, batch, classes, loss_out, dlogits, nullptr, (cudaStream_t)stream);
+    GUARD_END
+}
+int b2_ce_loss_grad_running(const float *logits, const int64_t *labels, int batch, int classes, float *loss_out, float *dlogits,
+                            float *running2, void *stream) {
+    GUARD_BEGIN
+    B2_CHECK(logits && labels && loss_out, B2_ERR_ARG, "b2_ce_loss_grad_running: NULL argument");
+    return op_ce_loss_grad(logits, labels, batch, classes, loss_out, dlogits, running2, (cudaStream_t)stream);
     GUARD_END
 }
 

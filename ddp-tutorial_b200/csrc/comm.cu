@@ -86,7 +86,10 @@ __device__ __forceinline__ void peer_barrier(const CommPtrs &P, int rank, uint32
         const uint32_t *mine = P.flags[rank] + ((phase * kMaxWorld + peer) * kFlagStride + blockIdx.x);
         long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
-            if (clock64() - t0 > 40000000000LL) { *err = 1; break; }   // ~20 s: fail, do not hang
+            // ~20 s without the peer: a rank died or diverged.  Continuing would reduce stale data and let the
+            // replicas drift apart silently, so record the reason and kill the context (every later CUDA call
+            // on this rank fails loudly; b2_comm_check() reports the flag when the host polls first).
+            if (clock64() - t0 > 40000000000LL) { *err = 1; __threadfence_system(); __trap(); }
         }
     }
     __syncthreads();

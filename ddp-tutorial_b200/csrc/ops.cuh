@@ -96,7 +96,7 @@ int conv_simt_wgrad(const ConvGeom &g, const void *x, const void *dy, int dt, fl
 
 // ---- loss / optimizer ------------------------------------------------------------------
 int op_ce_loss_grad(const float *logits, const int64_t *labels, int B, int C, float *loss,
-                    float *dlogits, cudaStream_t s);
+                    float *dlogits, float *running, cudaStream_t s);
 // pb (optional): bf16 mirror of p, written in the same pass
 int op_sgd(float *p, const float *g, float *m, int64_t n, float lr, float momentum, float gscale,
            int first, bf16 *pb, cudaStream_t s);

@@ -403,41 +403,64 @@ int op_bias_grad(const void *dy, int dt, int64_t M, int C, float *db, cudaStream
 // ---------------------------------------------------------------------------------
 // cross entropy (mean reduction) + softmax gradient, one kernel, one block
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_ce_loss_grad(const float *__restrict__ logits, const int64_t *__restrict__ labels, int B, int C,
-               float *__restrict__ loss, float *__restrict__ dlogits) {
+// Rows are staged through shared memory so that the global reads are coalesced (a row is only
+// C = 10 floats); one thread then owns one row.  `running` (optional, float[2]) accumulates
+// (sum of losses, count) on the device -- the reference's running_loss (cifar_example_ddp.py:110)
+// without a host read every step.  A label outside [0, C) traps (torch raises a device assert).
+constexpr int kCeRows = 512;
+__global__ void __launch_bounds__(kCeRows)
+k_ce_loss_grad(const float *__restrict__ logits, const int64_t *__restrict__ labels, int B, int C, int tile_rows,
+               float *__restrict__ loss, float *__restrict__ dlogits, float *__restrict__ running) {
     pdl_sync();
+    extern __shared__ float tile[];                 // [tile_rows][C], tile_rows <= kCeRows
+    __shared__ float sh[kCeRows / 32];
     float local = 0.f;
     const float invB = 1.f / (float)B;
-    for (int r = threadIdx.x; r < B; r += blockDim.x) {
-        const float *row = logits + (int64_t)r * C;
-        float mx = -INFINITY;
-        for (int j = 0; j < C; ++j) mx = fmaxf(mx, row[j]);
-        float se = 0.f;
-        for (int j = 0; j < C; ++j) se += expf(row[j] - mx);
-        float lse = logf(se);
-        int lab = (int)labels[r];
-        local += -(row[lab] - mx - lse);
-        if (dlogits) {
-            float *drow = dlogits + (int64_t)r * C;
-            for (int j = 0; j < C; ++j) {
-                float p = expf(row[j] - mx - lse);
-                drow[j] = (p - (j == lab ? 1.f : 0.f)) * invB;
+    for (int r0 = 0; r0 < B; r0 += tile_rows) {
+        const int rows = min(tile_rows, B - r0);
+        const float *src = logits + (int64_t)r0 * C;
+        for (int i = threadIdx.x; i < rows * C; i += kCeRows) tile[i] = src[i];
+        __syncthreads();
+        if ((int)threadIdx.x < rows) {
+            float *row = tile + threadIdx.x * C;
+            float mx = -INFINITY;
+            for (int j = 0; j < C; ++j) mx = fmaxf(mx, row[j]);
+            float se = 0.f;
+            for (int j = 0; j < C; ++j) se += expf(row[j] - mx);
+            const float lse = logf(se);
+            const long long lab = labels[r0 + threadIdx.x];
+            if (lab < 0 || lab >= C) {
+                printf("b2 cross_entropy: label %lld of row %d is outside [0, %d)\n", lab, r0 + (int)threadIdx.x, C);
+                __trap();
             }
+            local += -(row[lab] - mx - lse);
+            if (dlogits)
+                for (int j = 0; j < C; ++j) row[j] = (expf(row[j] - mx - lse) - (j == (int)lab ? 1.f : 0.f)) * invB;
         }
-    }
-    __shared__ float sh[256];
-    sh[threadIdx.x] = local;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+        if (dlogits) {
+            float *dst = dlogits + (int64_t)r0 * C;
+            for (int i = threadIdx.x; i < rows * C; i += kCeRows) dst[i] = tile[i];
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *loss = sh[0] * invB;
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < kCeRows / 32; ++w) t += sh[w];        // fixed order: deterministic
+        t *= invB;
+        *loss = t;
+        if (running) { running[0] += t; running[1] += 1.f; }
+    }
 }
-int op_ce_loss_grad(const float *logits, const int64_t *labels, int B, int C, float *loss, float *dlogits, cudaStream_t s) {
+int op_ce_loss_grad(const float *logits, const int64_t *labels, int B, int C, float *loss, float *dlogits, float *running,
+                    cudaStream_t s) {
     B2_CHECK(B > 0 && C > 0, B2_ERR_ARG, "ce: empty batch (B=%d, C=%d)", B, C);
-    B2_LAUNCH(k_ce_loss_grad, 1, 256, 0, s, logits, labels, B, C, loss, dlogits);
+    B2_CHECK(C <= 10240, B2_ERR_UNSUPPORTED, "ce: at most 10240 classes (row tile in shared memory), got %d", C);
+    int tile_rows = 10240 / C; if (tile_rows > kCeRows) tile_rows = kCeRows;        // <= 40 KB of shared memory
+    B2_LAUNCH(k_ce_loss_grad, 1, kCeRows, (size_t)tile_rows * C * sizeof(float), s, logits, labels, B, C, tile_rows, loss, dlogits, running);
     return 0;
 }
 

@@ -98,6 +98,8 @@ class Engine:
         self.flat_params_bf16: Optional[torch.Tensor] = None   # bf16 mirror shared by all batch sizes
         self.param_views: List[torch.Tensor] = []
         self._last_batch: Optional[int] = None
+        self._loss_seq = None      # sequence id of the forward the latest criterion() call consumed
+        self._fwd_seq = 0          # every forward gets a sequence id; backward() checks the Loss carries the latest
         self.ddp = None            # set by DistributedDataParallel
         self.optimizer = None      # set by SGD when built from our parameters
         self._keep = []            # objects that must outlive the vectors (comm allocations)
@@ -139,6 +141,12 @@ class Engine:
             raise B2Error("this engine runs on CUDA devices only (no CPU path)")
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
+        if self.device is not None:
+            # torch's .to(same device) is a no-op; re-running placement would reset trained
+            # parameters to the host init and (under DDP) detach them from the peer-mapped buffers
+            if dev == self.device:
+                return self
+            raise B2Error(f"model already lives on {self.device}; moving it to {dev} is not supported")
         self.device = dev
         self._probe_layout(dev.index)
         self._allocate(lambda n: torch.zeros(n, dtype=torch.float32, device=dev))
@@ -206,13 +214,20 @@ class Engine:
             self._logits[x.shape[0]] = logits
         call("b2_forward", m.h, C.c_void_p(x.data_ptr()), C.c_void_p(logits.data_ptr()), _stream_ptr())
         self._last_batch = x.shape[0]
+        self._fwd_seq += 1
         logits._b2_engine = self
+        logits._b2_seq = self._fwd_seq
         logits._b2_input = x          # keep the input alive until backward has been enqueued
         return logits
 
-    def backward(self, dlogits: torch.Tensor):
+    def backward(self, dlogits: torch.Tensor, seq: Optional[int] = None):
         if self._last_batch is None:
             raise B2Error("backward() before forward()")
+        if seq is not None and seq != self._fwd_seq:
+            raise B2Error("backward() of a stale loss: another forward ran after the one this loss belongs to "
+                          "(the graph is static and keeps only the latest forward's activations)")
+        if dlogits.shape[0] != self._last_batch:
+            raise B2Error("backward(): dlogits batch does not match the latest forward")
         m = self._model(self._last_batch)
         if self.ddp is not None:
             self.ddp._before_backward(m)

@@ -222,14 +222,18 @@ class Loss:
     """Result of ``criterion(outputs, labels)``: supports ``backward()`` and ``item()``
     (cifar_example_ddp.py:105,106,110)."""
 
-    def __init__(self, engine: Engine, value: torch.Tensor, dlogits: torch.Tensor, keep):
+    def __init__(self, engine: Engine, value: torch.Tensor, dlogits: torch.Tensor, keep, seq=None):
         self._engine, self._value, self._dlogits, self._keep = engine, value, dlogits, keep
+        self._seq = seq
         self._done = False
 
     def backward(self):
         if self._done:
             raise B2Error("backward() called twice on the same loss (the graph is static; run forward again)")
-        self._engine.backward(self._dlogits)
+        if self._seq is not None and self._seq != self._engine._loss_seq:
+            raise B2Error("backward() of a stale loss: criterion() was called again after this loss was created "
+                          "(the softmax-gradient buffer is shared per batch size)")
+        self._engine.backward(self._dlogits, self._seq)
         self._done = True
 
     def item(self) -> float:
@@ -245,12 +249,29 @@ class Loss:
         return self._value
 
 
-class CrossEntropyLoss:
-    """``nn.CrossEntropyLoss()`` with default arguments (mean reduction)."""
+class RunningLoss:
+    """Device-side ``running_loss`` of the reference's print cadence (cifar_example_ddp.py:110-114):
+    the criterion kernel adds every step's loss to a device accumulator; the host reads it only when
+    it prints (every ``print_every`` steps) instead of synchronising on ``loss.item()`` every step."""
 
-    def __init__(self, reduction: str = "mean"):
+    def __init__(self, device):
+        dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.acc = torch.zeros(2, dtype=torch.float32, device=dev)        # [sum of losses, count]
+
+    def mean_and_reset(self) -> float:
+        s, n = self.acc.tolist()                                           # one device->host read + sync
+        self.acc.zero_()
+        return s / n if n else 0.0
+
+
+class CrossEntropyLoss:
+    """``nn.CrossEntropyLoss()`` with default arguments (mean reduction).  ``running``: optional
+    :class:`RunningLoss` that accumulates the loss of every call on the device."""
+
+    def __init__(self, reduction: str = "mean", running: Optional[RunningLoss] = None):
         if reduction != "mean":
             raise B2Error("only the reference's default reduction='mean' is implemented")
+        self.running = running
 
     def __call__(self, outputs: torch.Tensor, labels: torch.Tensor) -> Loss:
         engine = getattr(outputs, "_b2_engine", None)
@@ -263,6 +284,12 @@ class CrossEntropyLoss:
         labels = labels.contiguous()
         loss = torch.empty(1, dtype=torch.float32, device=outputs.device)
         dlogits = engine.dlogits_buffer(outputs.shape[0])
-        call("b2_ce_loss_grad", C.c_void_p(outputs.data_ptr()), C.c_void_p(labels.data_ptr()), outputs.shape[0],
-             outputs.shape[1], C.c_void_p(loss.data_ptr()), C.c_void_p(dlogits.data_ptr()), _stream_ptr())
-        return Loss(engine, loss, dlogits, (outputs, labels))
+        run = self.running
+        if run is not None and run.acc.device != outputs.device:
+            raise B2Error(f"running-loss accumulator on {run.acc.device}, outputs on {outputs.device}")
+        call("b2_ce_loss_grad_running", C.c_void_p(outputs.data_ptr()), C.c_void_p(labels.data_ptr()), outputs.shape[0],
+             outputs.shape[1], C.c_void_p(loss.data_ptr()), C.c_void_p(dlogits.data_ptr()),
+             C.c_void_p(run.acc.data_ptr()) if run is not None else None, _stream_ptr())
+        seq = getattr(outputs, "_b2_seq", None)
+        engine._loss_seq = seq
+        return Loss(engine, loss, dlogits, (outputs, labels), seq)

@@ -176,9 +176,13 @@ class DistributedDataParallel:
 
     def _attach_optimizer(self, opt):
         """Called when an SGD is built over this model's parameters (cifar_example_ddp.py:86)."""
-        if not self.overlap:
-            return
         e = self.engine
+        if not self.overlap:
+            # an SGD built before the wrapper armed its own fused update inside backward(); under DDP the
+            # update belongs to the exchange kernel at step(), so disarm it (otherwise two updates per step)
+            for m in e.models.values():
+                call("b2_model_set_fused_sgd", m.h, 0, None, 0.0, 0.0, 0)
+            return
         for m in e.models.values():
             self._configure_model(m, opt)
 
@@ -243,9 +247,14 @@ def barrier() -> None:
         call("b2_comm_barrier", _stream_ptr())
 
 
-def check() -> None:
+def check(*models) -> None:
+    """Synchronises and raises ``B2Error`` if a peer flag wait of the communicator or a grid barrier of any
+    of ``models`` (modules or DDP wrappers) timed out.  (A timeout also traps the kernel, so the next CUDA
+    call fails as well; this is the cheap explicit poll for training loops.)"""
     if _state["comm"]:
         call("b2_comm_check")
+    for m in models:
+        m.engine.check()
 
 
 def destroy() -> None:

@@ -142,6 +142,11 @@ int b2_argmax_count(const float *logits, const int64_t *labels, int batch, int c
 /* ---- criterion: nn.CrossEntropyLoss() fwd+bwd (cifar_example_ddp.py:85,105) -- */
 int b2_ce_loss_grad(const float *logits, const int64_t *labels, int batch, int classes,
                     float *loss_out, float *dlogits, void *stream);
+/* same, and additionally running2[0] += loss, running2[1] += 1 on the device: the reference's
+ * `running_loss += loss.item()` (cifar_example_ddp.py:110) without a host sync every step; the
+ * caller reads running2 back every print interval (:111-114).  running2 may be NULL. */
+int b2_ce_loss_grad_running(const float *logits, const int64_t *labels, int batch, int classes,
+                            float *loss_out, float *dlogits, float *running2, void *stream);
 
 /* ---- optimizer: optim.SGD(lr, momentum).step() (cifar_example_ddp.py:86,107) -- */
 /* p,g,m fp32 [n]; first_step!=0 => m = g (sgd.py:_single_tensor_sgd clones the
