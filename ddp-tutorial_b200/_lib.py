@@ -49,6 +49,7 @@ _SIGS = {
     "b2_preprocess_u8": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp]),
     "b2_argmax_count": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "b2_conv_test": (_i, [_i] * 11 + [_vp, _vp, _vp, _vp, _vp]),
+    "b2_conv_bn_test": (_i, [_i] * 9 + [_vp] * 11),
     "b2_ce_loss_grad": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "b2_ce_loss_grad_running": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "b2_sgd": (_i, [_vp, _vp, _vp, _i64, _f, _f, _f, _i, _vp, _vp]),

@@ -275,8 +275,8 @@ int b2_conv_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, int p
             else if (mode == 0) { UmmaConvPlan pl; rc = umma_plan_fprop(g, (const bf16 *)x_bf16, w, (bf16 *)out, &pl); if (!rc) rc = umma_conv_launch(pl, s); }
             else if (mode == 1) { UmmaConvPlan pl; rc = umma_plan_dgrad(g, (const bf16 *)dy_bf16, w, (bf16 *)out, acc != 0, &pl); if (!rc) rc = umma_conv_launch(pl, s); }
             else {
-                UmmaWgradPlan pl; rc = umma_plan_wgrad(g, (const bf16 *)x_bf16, (const bf16 *)dy_bf16, (float *)out, ws, wsf, &pl);
-                if (!rc) rc = umma_wgrad_zero_dead(pl, s);
+                UmmaWgradPlan pl; rc = umma_plan_wgrad(g, (const bf16 *)x_bf16, (const bf16 *)dy_bf16, (float *)out, ws, wsf, acc != 0 /* deterministic */, &pl);
+                if (!rc && (pl.p.atomic || pl.need_zero)) { cudaError_t ze = cudaMemsetAsync(out, 0, (size_t)Co * taps * Ci * 4, s); if (ze != cudaSuccess) rc = B2_ERR_CUDA; }
                 if (!rc) rc = umma_wgrad_launch(pl, s);
             }
         } else {
@@ -288,6 +288,46 @@ int b2_conv_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, int p
     cudaError_t e = cudaStreamSynchronize(s);
     cudaFree(w); cudaFree(wt); cudaFree(ws);
     if (rc == 0 && e != cudaSuccess) { set_error("conv_test: %s", cudaGetErrorString(e)); rc = B2_ERR_CUDA; }
+    return rc;
+    GUARD_END
+}
+
+
+// ---- kernel-level test entry: fprop with the fused BatchNorm(+residual, ReLU) epilogue -------------
+// (the launch bench.py times for every conv+BN pair).  x: bf16 NHWC, w: fp32 O,H,W,I, res: bf16 NHWC of the
+// output shape or NULL, gamma/beta: fp32 [Co].  Outputs: z = conv(x) (bf16), y = relu?(bn(z) + res) (bf16),
+// mean / invstd (fp32 [Co]) of the training-mode batch statistics.
+int b2_conv_bn_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, int pad, int relu, const void *x_bf16,
+                    const float *w_master, const void *res_bf16, const float *gamma, const float *beta, void *z_out, void *y_out,
+                    float *mean_out, float *invstd_out, int *info3, void *stream) {
+    GUARD_BEGIN
+    cudaStream_t s = (cudaStream_t)stream;
+    ConvGeom g{};
+    g.N = N; g.Hi = Hi; g.Wi = Wi; g.Ci = Ci; g.Co = Co; g.kh = g.kw = k; g.stride = stride; g.pad = pad;
+    g.Ho = (Hi + 2 * pad - k) / stride + 1; g.Wo = (Wi + 2 * pad - k) / stride + 1;
+    B2_CHECK(umma_conv_eligible(g), B2_ERR_UNSUPPORTED, "conv_bn_test: shape not eligible for the tcgen05 path");
+    bf16 *w = nullptr; float *scratch = nullptr;
+    const size_t wn = (size_t)Co * k * k * Ci, sums = 2 * (size_t)kBnSumCopies * Co;
+    B2_CUDA(cudaMalloc(&w, wn * 2));
+    B2_CUDA(cudaMalloc(&scratch, (sums + 8) * 4));
+    B2_CUDA(cudaMemsetAsync(scratch, 0, (sums + 8) * 4, s));
+    int rc = op_f32_to_bf16(w_master, w, (int64_t)wn, s);
+    UmmaConvPlan pl;
+    if (!rc) rc = umma_plan_fprop(g, (const bf16 *)x_bf16, w, (bf16 *)z_out, &pl);
+    if (!rc) rc = umma_conv_check_coresident(pl);
+    if (!rc) {
+        ConvParams &q = pl.p;
+        q.stats = scratch;
+        q.fuse_bn = 1; q.fb_y = (bf16 *)y_out; q.fb_res = (const bf16 *)res_bf16; q.fb_gamma = gamma; q.fb_beta = beta;
+        q.fb_save_mean = mean_out; q.fb_save_invstd = invstd_out; q.fb_running_mean = nullptr; q.fb_running_var = nullptr;
+        q.fb_sync = (unsigned int *)(scratch + sums); q.fb_err = (int *)(scratch + sums + 4);
+        q.fb_count = (float)g.M(); q.fb_eps = 1e-5f; q.fb_momentum = 0.1f; q.fb_relu = relu ? 1 : 0;
+        if (info3) { info3[0] = pl.bn_tile; info3[1] = pl.grid; info3[2] = pl.p.total_tiles; }
+        rc = umma_conv_launch(pl, s);
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(w); cudaFree(scratch);
+    if (rc == 0 && e != cudaSuccess) { set_error("conv_bn_test: %s", cudaGetErrorString(e)); rc = B2_ERR_CUDA; }
     return rc;
     GUARD_END
 }

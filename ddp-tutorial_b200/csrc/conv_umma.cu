@@ -9,11 +9,18 @@
 // (element strides {1,s,s,1} for a strided conv); out-of-bounds pixels are zero-filled by the
 // TMA unit, which is exactly the convolution's zero padding.  No im2col buffer ever exists.
 //
-//   fprop / dgrad  (k_tapgemm): D[128 pix][64 ch] += A_tap[128 pix][64 k] * W_tap[64 ch][64 k]^T
-//       A, B K-major SWIZZLE_128B tiles, UMMA 128x64x16, fp32 accumulators in TMEM,
-//       warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (TMEM -> bf16 -> HBM)
+//   fprop / dgrad  (k_conv<BN_TILE>): D[128 pix][BN_TILE ch] += A_tap[128 pix][64 k] * W_tap[BN_TILE ch][64 k]^T
+//       persistent: grid <= #SMs, CTA b walks tiles b, b+grid, ...; accumulators double-buffered in TMEM so the
+//       epilogue of tile i overlaps the main loop of tile i+1.  Warp roles: 0 = TMA producer of A,
+//       1 = TMA producer of B (measured, tools/tma_bench3.cu: the TMA unit processes the boxes of ONE issuing
+//       warp back to back at ~2 clk per 128-byte row, but streams from two warps overlap: 16 KB A + 16 KB B per
+//       k-step in ~260-330 clk instead of ~540), 2 = MMA issuer, 3-6 = epilogue.
+//       Epilogue: TMEM -> bf16 -> 128B-swizzled staging tile in shared memory -> row-coalesced 16-byte global
+//       stores; the same pass accumulates per-channel BatchNorm sums (forward statistics, or the backward sums
+//       sum(g), sum(g*xhat) of the BatchNorm that produced the tensor whose gradient this dgrad finalises).
 //   wgrad (k_wgrad): dW[co][k] += dY[pix][co]^T * X_tap[pix][k]: both operands MN-major
-//       (the contraction runs over pixels, i.e. over tile rows), split over pixel tiles.
+//       (the contraction runs over pixels, i.e. over tile rows), split over pixel tiles; the splits add into
+//       dW with red.global.add.v4.f32 (or, deterministic mode, through partials + a reduce kernel).
 #include <mutex>
 #include <algorithm>
 #include <stdlib.h>
@@ -30,6 +37,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
+static int g_num_sms = 0;
 
 int umma_init() {
     if (g_encode) return 0;
@@ -37,9 +45,13 @@ int umma_init() {
     cudaDriverEntryPointQueryResult qres;
     B2_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     B2_CHECK(fn && qres == cudaDriverEntryPointSuccess, B2_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+    int dev = 0;
+    B2_CUDA(cudaGetDevice(&dev));
+    B2_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     g_encode = (EncodeTiledFn)fn;
     return 0;
 }
+int umma_num_sms() { return g_num_sms > 0 ? g_num_sms : kNumSMs; }
 
 // NHWC bf16 tensor [N][H][W][C]: box {64, bw*es, bh*es, bn}, element strides {1, es, es, 1}
 static int make_map_nhwc(CUtensorMap *m, const void *base, int N, int H, int W, int C, int bw, int bh, int bn, int es) {
@@ -81,6 +93,7 @@ static bool tile_geometry(int N, int Hb, int Wb, int *BW, int *BH, int *BN) {
     *BW = bw; *BH = bh; *BN = bn;
     return true;
 }
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 bool umma_conv_eligible(const ConvGeom &g) {
     if (g.Ci % 64 || g.Co % 64) return false;
@@ -103,49 +116,58 @@ static bool tap_alive(int d, int step, int nbox, int src) {
 // =================================================================================
 // device: fprop / dgrad
 // =================================================================================
-constexpr int kATileBytes = 128 * 128;       // 128 pixel rows x 64 bf16
-constexpr int kBTileBytes = 64 * 128;        // 64 channel rows x 64 bf16
-// Pipeline depth: the per-SM load rate is bytes-in-flight / L2 latency, so a grid that gives each SM
-// one CTA needs a deep ring (8 stages = 192 KB in flight); grids with >= 2 CTAs per SM use 4 stages
-// (96 KB each) so that two CTAs co-reside and overlap one's epilogue with the other's main loop.
-// SPLIT: a cluster of two CTAs shares one output tile, each running half of the K steps (doubles the
-// number of SMs pulling operands for layers whose grid is smaller than the chip); CTA 1 hands its
-// fp32 accumulators to CTA 0 through distributed shared memory, CTA 0 runs the epilogue.
-constexpr int kSplitStageBytes = 128 * 68 * 4;      // [128 rows][64 + 4 pad] fp32
-constexpr int tap_smem(int stages, bool split = false) {
-    return stages * (kATileBytes + kBTileBytes) + (split ? kSplitStageBytes : 0) + 1024 /*align*/ + 256 /*barriers*/;
+template <int BN_TILE>
+struct ConvCfg {
+    static constexpr int kStages = BN_TILE == 128 ? 5 : 6;
+    static constexpr int kABytes = 128 * 128;              // 128 pixel rows x 64 bf16
+    static constexpr int kBBytes = BN_TILE * 128;          // BN_TILE channel rows x 64 bf16 (or 64 k-rows x BN_TILE)
+    static constexpr int kStagingBytes = (BN_TILE / 64) * 16384;   // [half][128 rows][128 B], 128B-swizzled
+    static constexpr int kRedFloats = 4 * 2 * BN_TILE;     // per epilogue warp: [2][BN_TILE] partial sums
+    static constexpr int kSmem = kStages * (kABytes + kBBytes) + kStagingBytes + (kRedFloats + 2 * BN_TILE) * 4 + 256 /*barriers*/ + 1024 /*align*/;
+    static constexpr int kTmemCols = 2 * BN_TILE;          // two accumulator buffers
+    static constexpr int kCPR = BN_TILE / 8;               // 16-byte chunks per output row
+};
+constexpr int kConvThreads = 224;     // warps: 0 A-TMA, 1 B-TMA, 2 MMA, 3..6 epilogue
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct TileCoord { int z, n, n_blk, h_blk, ch0, m; };
+template <int BN_TILE>
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams &p, int t) {
+    TileCoord c;
+    c.m = t % p.m_tiles;
+    const int r = t / p.m_tiles;
+    c.n = r % p.n_tiles; c.z = r / p.n_tiles;
+    c.n_blk = c.m / p.h_blocks; c.h_blk = c.m - c.n_blk * p.h_blocks;
+    c.ch0 = c.n * BN_TILE;
+    return c;
 }
 
-template <int kStagesTap, bool SPLIT>
-__global__ void __launch_bounds__(192)
-k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
-          const __grid_constant__ TapGemmParams p) {
+template <int BN_TILE>
+__global__ void __launch_bounds__(kConvThreads, 1)
+k_conv(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
+       const __grid_constant__ ConvParams p) {
+    using Cfg = ConvCfg<BN_TILE>;
+    constexpr int S = Cfg::kStages, kA = Cfg::kABytes, kB = Cfg::kBBytes, CPR = Cfg::kCPR;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
-    uint8_t *sB = smem + kStagesTap * kATileBytes;
-    float *sX = (float *)(sB + kStagesTap * kBTileBytes);                 // SPLIT: partner's accumulators land here
-    uint64_t *bars = (uint64_t *)((uint8_t *)sX + (SPLIT ? kSplitStageBytes : 0));
-    uint64_t *full = bars, *empty = bars + kStagesTap, *tmem_full = bars + 2 * kStagesTap;
-    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * kStagesTap + 1);
+    uint8_t *sB = sA + S * kA;
+    uint8_t *sStage = sB + S * kB;                                   // epilogue staging tile
+    float *sRed = (float *)(sStage + Cfg::kStagingBytes);            // [4 warps][2][BN_TILE]
+    float *sSS = sRed + Cfg::kRedFloats;                             // scale[BN_TILE], shift[BN_TILE]
+    uint64_t *bars = (uint64_t *)(sSS + 2 * BN_TILE);
+    uint64_t *full = bars, *empty = bars + S, *tfull = bars + 2 * S, *tempty = bars + 2 * S + 2;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * S + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const TapClass &cls = p.cls[blockIdx.z];
-    const uint32_t crank = SPLIT ? cluster_ctarank() : 0u;
-    const int tile_x = SPLIT ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int n_blk = tile_x / p.h_blocks, h_blk = tile_x % p.h_blocks;
-    const int ch0 = blockIdx.y * 64;
-    const int ksteps_all = cls.ntaps * p.c_chunks;
-    const int ks_begin = SPLIT ? (crank == 0 ? 0 : (ksteps_all + 1) / 2) : 0;
-    const int ks_end = SPLIT ? (crank == 0 ? (ksteps_all + 1) / 2 : ksteps_all) : ksteps_all;
-
-    if (warp == 0 && lane == 0) {
+    if (threadIdx.x == 0) {
         prefetch_tmap(&a_map); prefetch_tmap(&b_map);
-        for (int i = 0; i < kStagesTap; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(tmem_full, 1);
+        for (int i = 0; i < S; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
         fence_barrier_init();
     }
-    if (warp == 1) { tmem_alloc(tmem_slot, 64); tmem_relinquish(); }
+    if (warp == 2) { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
     pdl_trigger();                 // the next kernel may begin its own prologue
     tc_fence_before();
     __syncthreads();
@@ -154,206 +176,271 @@ k_tapgemm(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUt
     pdl_wait();                    // everything below touches global memory of earlier kernels
 
     if (warp == 0) {
+        // ---------------- TMA producer: activation (A) tiles
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int ks = ks_begin; ks < ks_end; ++ks) {
-                const int tap = ks / p.c_chunks, cc = ks - tap * p.c_chunks;
-                mbar_wait(&empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full[stage], kATileBytes + kBTileBytes);
-                tma_load_4d(sA + stage * kATileBytes, &a_map, &full[stage], cc * 64, cls.dw[tap],
-                            h_blk * p.BH * p.a_hstep + cls.dh[tap], n_blk * p.BN);
-                if (p.b_mn) tma_load_2d(sB + stage * kBTileBytes, &b_map, &full[stage], cls.kofs[tap] + ch0, cc * 64);
-                else tma_load_2d(sB + stage * kBTileBytes, &b_map, &full[stage], cls.kofs[tap] + cc * 64, ch0);
-                if (++stage == kStagesTap) { stage = 0; phase ^= 1; }
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile<BN_TILE>(p, t);
+                const TapClass &cls = p.cls[tc.z];
+                const int ksteps = cls.ntaps * p.c_chunks;
+                int tap = 0, cc = 0;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], kA);
+                    tma_load_4d(sA + stage * kA, &a_map, &full[stage], cc * 64, cls.dw[tap],
+                                tc.h_blk * p.BH * p.a_hstep + cls.dh[tap], tc.n_blk * p.BN);
+                    if (++cc == p.c_chunks) { cc = 0; ++tap; }
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
+        // ---------------- TMA producer: weight (B) tiles
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 64, 0, p.b_mn);
-            const uint32_t bstep = p.b_mn ? 2048 : 32;     // 16 K-rows of 128 B vs 16 K-elements
             int stage = 0; uint32_t phase = 0;
-            for (int ks = ks_begin; ks < ks_end; ++ks) {
-                mbar_wait(&full[stage], phase);
-                tc_fence_after();
-                const uint32_t a0 = smem_u32(sA + stage * kATileBytes), b0 = smem_u32(sB + stage * kBTileBytes);
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile<BN_TILE>(p, t);
+                const TapClass &cls = p.cls[tc.z];
+                const int ksteps = cls.ntaps * p.c_chunks;
+                int tap = 0, cc = 0;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], kB);
+                    uint8_t *dst = sB + stage * kB;
+                    if (p.b_mn) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    mma_bf16_ss(tmem_base, make_desc_sw128(a0 + k * 32, 16, 1024),
-                                make_desc_sw128(b0 + k * bstep, kBTileBytes, 1024), idesc, (ks > ks_begin || k > 0) ? 1u : 0u);
+                        for (int j = 0; j < BN_TILE / 64; ++j)
+                            tma_load_2d(dst + j * 8192, &b_map, &full[stage], cls.kofs[tap] + tc.ch0 + j * 64, cc * 64);
+                    } else {
+                        tma_load_2d(dst, &b_map, &full[stage], cls.kofs[tap] + cc * 64, tc.ch0);
+                    }
+                    if (++cc == p.c_chunks) { cc = 0; ++tap; }
+                    if (++stage == S) { stage = 0; phase ^= 1; }
                 }
-                mma_commit(&empty[stage]);
-                if (++stage == kStagesTap) { stage = 0; phase ^= 1; }
             }
-            mma_commit(tmem_full);
+        }
+    } else if (warp == 2) {
+        // ---------------- MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, BN_TILE, 0, p.b_mn);
+            const uint32_t bstep = p.b_mn ? 2048 : 32;     // 16 K-rows of 128 B vs 16 K-elements
+            const uint32_t blbo = p.b_mn ? 8192 : kB;      // MN-major: distance between 64-channel atoms
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+                const TileCoord tc = decode_tile<BN_TILE>(p, t);
+                const int ksteps = p.cls[tc.z].ntaps * p.c_chunks;
+                const int buf = it & 1;
+                mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * BN_TILE;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(sA + stage * kA), b0 = smem_u32(sB + stage * kB);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        mma_bf16_ss(d_tmem, make_desc_sw128(a0 + k * 32, 16, 1024), make_desc_sw128(b0 + k * bstep, blbo, 1024), idesc,
+                                    (ks > 0 || k > 0) ? 1u : 0u);
+                    mma_commit(&empty[stage]);
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+                mma_commit(&tfull[buf]);
+            }
         }
     } else {
-        // ---- epilogue: TMEM lane quarter (warp % 4) -> rows
-        const int q = warp & 3;
-        const int r = q * 32 + lane;
-        const int w_l = r % p.BW; const int t = r / p.BW;
-        const int h_l = t % p.BH; const int n_l = t / p.BH;
-        const int n = n_blk * p.BN + n_l;
-        const int h = (h_blk * p.BH + h_l) * p.os + cls.oh;
-        const int w = w_l * p.os + cls.ow;
-        bf16 *dst = p.out + (((int64_t)n * p.out_H + h) * p.out_W + w) * p.out_C + ch0;
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        uint32_t v[32];
-        if (SPLIT && crank == 1) {
-            // hand this CTA's partial accumulators to CTA 0 (its sX), then leave through the cluster barrier
-            const uint32_t remote = map_to_cta(smem_u32(sX), 0) + (uint32_t)r * 68 * 4;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + half * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    st_cluster_f4(remote + (half * 32 + j * 4) * 4, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            }
-            cluster_arrive();
-            cluster_wait();
-        } else {
-        if (SPLIT) { cluster_arrive(); cluster_wait(); }       // partner's accumulators are in sX now
-        float *sT = (float *)sA;                       // [128][65] fp32 staging for per-channel sums
-        float *sT2 = sT + 128 * 65;                    // second plane (spills into the B stages: 66.5 KB < 96 KB)
+        // ---------------- epilogue (128 threads)
+        const int q = warp & 3;                          // TMEM lane quarter this warp may read
+        const int r = q * 32 + lane;                     // phase A: this thread owns tile row r
+        const int et = (warp - 3) * 32 + lane;           // phase B: linear id 0..127
+        const int chunk = et % CPR, rsub = et / CPR;     // phase B: fixed 8-channel chunk, rows rsub + i * (128 / CPR)
+        const int half = chunk >> 3, c8 = chunk & 7;
         const bool want_fwd = p.stats != nullptr, want_bwd = p.bn_bsum != nullptr;
-        const int64_t pix_off = (((int64_t)n * p.out_H + h) * p.out_W + w) * p.out_C + ch0;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            const TileCoord tc = decode_tile<BN_TILE>(p, t);
+            const TapClass &cls = p.cls[tc.z];
+            const int buf = it & 1;
+            mbar_wait(&tfull[buf], (it >> 1) & 1);
+            tc_fence_after();
+            // ---- phase A: TMEM -> bf16 -> swizzled staging rows
+            {
+                uint8_t *row_base = sStage + r * 128;
+                const int sw = r & 7;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + half * 32, v);
-            tmem_ld_wait();
-            uint4 *d4 = (uint4 *)(dst + half * 32);
+                for (int j = 0; j < BN_TILE / 32; ++j) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + buf * BN_TILE + ((uint32_t)(q * 32) << 16) + j * 32, v);
+                    tmem_ld_wait();
+                    uint8_t *hb = row_base + (j >> 1) * 16384;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float f[8];
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        uint4 pk;
+                        __nv_bfloat162 *p2 = (__nv_bfloat162 *)&pk;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]);
-                if (SPLIT) {
-                    const float4 x0 = *(const float4 *)(sX + r * 68 + half * 32 + j * 8);
-                    const float4 x1 = *(const float4 *)(sX + r * 68 + half * 32 + j * 8 + 4);
-                    f[0] += x0.x; f[1] += x0.y; f[2] += x0.z; f[3] += x0.w; f[4] += x1.x; f[5] += x1.y; f[6] += x1.z; f[7] += x1.w;
+                        for (int e = 0; e < 4; ++e)
+                            p2[e] = __floats2bfloat162_rn(__uint_as_float(v[k4 * 8 + 2 * e]), __uint_as_float(v[k4 * 8 + 2 * e + 1]));
+                        const int cidx = (j & 1) * 4 + k4;                 // 16-byte chunk within the 128-byte half row
+                        *(uint4 *)(hb + ((cidx ^ sw) << 4)) = pk;
+                    }
                 }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);        // the MMA warp may start tile it+2 into this buffer
+            epi_bar();
+            // ---- phase B: row-coalesced stores (+ read-modify-write, + BatchNorm sums)
+            float s0[8], s1[8], mu[8], is[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { s0[e] = 0.f; s1[e] = 0.f; }
+            if (want_bwd) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { mu[e] = __ldg(p.bn_mean + tc.ch0 + chunk * 8 + e); is[e] = __ldg(p.bn_invstd + tc.ch0 + chunk * 8 + e); }
+            }
+#pragma unroll 4
+            for (int i = 0; i < CPR; ++i) {
+                const int row = rsub + i * (128 / CPR);
+                const int w_l = row & (p.BW - 1);
+                const int tt = row >> p.lgBW;
+                const int h_l = tt & (p.BH - 1), n_l = tt >> p.lgBH;
+                const int n = tc.n_blk * p.BN + n_l;
+                const int h = (tc.h_blk * p.BH + h_l) * p.os + cls.oh;
+                const int w = w_l * p.os + cls.ow;
+                const int64_t off = (((int64_t)n * p.out_H + h) * p.out_W + w) * p.out_C + tc.ch0 + chunk * 8;
+                uint4 pk = *(const uint4 *)(sStage + half * 16384 + row * 128 + ((c8 ^ (row & 7)) << 4));
+                __nv_bfloat162 *p2 = (__nv_bfloat162 *)&pk;
                 if (p.acc) {
-                    uint4 old = d4[j];
+                    const uint4 old = *(const uint4 *)(p.out + off);
                     const __nv_bfloat162 *o2 = (const __nv_bfloat162 *)&old;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) { float2 of = __bfloat1622float2(o2[e]); f[2 * e] += of.x; f[2 * e + 1] += of.y; }
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 a = __bfloat1622float2(p2[e]), b = __bfloat1622float2(o2[e]);
+                        p2[e] = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+                    }
                 }
-                uint4 pk;
-                __nv_bfloat162 *p2 = (__nv_bfloat162 *)&pk;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) p2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-                d4[j] = pk;
-                const int col = half * 32 + j * 8;
+                *(uint4 *)(p.out + off) = pk;
                 if (want_fwd) {                        // statistics of the values BatchNorm will read (bf16-rounded)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        float2 rf = __bfloat1622float2(p2[e]);
-                        sT[r * 65 + col + 2 * e] = rf.x;
-                        sT[r * 65 + col + 2 * e + 1] = rf.y;
+                        const float2 f = __bfloat1622float2(p2[e]);
+                        s0[2 * e] += f.x; s1[2 * e] = fmaf(f.x, f.x, s1[2 * e]);
+                        s0[2 * e + 1] += f.y; s1[2 * e + 1] = fmaf(f.y, f.y, s1[2 * e + 1]);
                     }
-                }
-                if (want_bwd) {                        // g = dY*[y>0],  g*xhat  of the BatchNorm that produced this tensor
-                    uint4 yr = *(const uint4 *)(p.bn_y + pix_off + col), xr = *(const uint4 *)(p.bn_x + pix_off + col);
+                } else if (want_bwd) {                 // g = dY*[y>0],  g*xhat  of the BatchNorm that produced this tensor
+                    const uint4 yr = *(const uint4 *)(p.bn_y + off), xr = *(const uint4 *)(p.bn_x + off);
                     const __nv_bfloat162 *y2 = (const __nv_bfloat162 *)&yr, *x2 = (const __nv_bfloat162 *)&xr;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        float2 g = __bfloat1622float2(p2[e]), yv = __bfloat1622float2(y2[e]), xv = __bfloat1622float2(x2[e]);
-                        const int c = ch0 + col + 2 * e;
+                        float2 g = __bfloat1622float2(p2[e]);
+                        const float2 yv = __bfloat1622float2(y2[e]), xv = __bfloat1622float2(x2[e]);
                         if (p.bn_relu) { if (!(yv.x > 0.f)) g.x = 0.f; if (!(yv.y > 0.f)) g.y = 0.f; }
-                        sT[r * 65 + col + 2 * e] = g.x;
-                        sT[r * 65 + col + 2 * e + 1] = g.y;
-                        sT2[r * 65 + col + 2 * e] = g.x * ((xv.x - __ldg(p.bn_mean + c)) * __ldg(p.bn_invstd + c));
-                        sT2[r * 65 + col + 2 * e + 1] = g.y * ((xv.y - __ldg(p.bn_mean + c + 1)) * __ldg(p.bn_invstd + c + 1));
+                        s0[2 * e] += g.x; s1[2 * e] = fmaf(g.x, (xv.x - mu[2 * e]) * is[2 * e], s1[2 * e]);
+                        s0[2 * e + 1] += g.y; s1[2 * e + 1] = fmaf(g.y, (xv.y - mu[2 * e + 1]) * is[2 * e + 1], s1[2 * e + 1]);
                     }
                 }
             }
-        }
-        const int e = (warp - 2) * 32 + lane;
-        if (want_fwd || want_bwd) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
-            const int c = e & 63, r0 = (e >> 6) * 64;
-            float s0 = 0.f, s1 = 0.f;
-            if (want_fwd) {
-#pragma unroll 8
-                for (int rr = 0; rr < 64; ++rr) { float x = sT[(r0 + rr) * 65 + c]; s0 += x; s1 = fmaf(x, x, s1); }
-            } else {
-#pragma unroll 8
-                for (int rr = 0; rr < 64; ++rr) { s0 += sT[(r0 + rr) * 65 + c]; s1 += sT2[(r0 + rr) * 65 + c]; }
+            if (want_fwd || want_bwd) {
+                // lanes with equal (lane % CPR) own the same channels: butterfly over the others, then over the 4 warps
+#pragma unroll
+                for (int o = CPR; o < 32; o <<= 1) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { s0[e] += __shfl_xor_sync(0xffffffffu, s0[e], o); s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o); }
+                }
+                float *mine = sRed + (warp - 3) * 2 * BN_TILE;
+                if (lane < CPR) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { mine[lane * 8 + e] = s0[e]; mine[BN_TILE + lane * 8 + e] = s1[e]; }
+                }
+                epi_bar();
+                float *dst = (want_fwd ? p.stats : p.bn_bsum) + (size_t)(blockIdx.x % kBnSumCopies) * 2 * p.out_C;
+                for (int j = et; j < 2 * BN_TILE; j += 128) {
+                    const float v = sRed[j] + sRed[2 * BN_TILE + j] + sRed[4 * BN_TILE + j] + sRed[6 * BN_TILE + j];
+                    const int which = j / BN_TILE, c = j - which * BN_TILE;
+                    atomicAdd(dst + which * p.out_C + tc.ch0 + c, v);
+                }
             }
-            float *st = (want_fwd ? p.stats : p.bn_bsum) + (size_t)((blockIdx.x + blockIdx.z) % kBnSumCopies) * 2 * p.out_C;
-            atomicAdd(st + ch0 + c, s0);
-            atomicAdd(st + p.out_C + ch0 + c, s1);
+            epi_bar();                                     // staging tile and sRed are free again
         }
         if (p.fuse_bn) {
-            // ---- grid-wide barrier: every CTA of this launch has contributed its tile's sums
+            // ---- grid-wide barrier: every CTA of this launch has stored its tiles and contributed its sums
             __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (e == 0) {
-                atomicAdd(p.fb_counter, 1u);
-                const uint32_t total = gridDim.x * gridDim.y * gridDim.z;
-                const long long t0 = clock64();
-                while (ld_acquire_gpu_u32(p.fb_counter) < total)
-                    if (clock64() - t0 > 6000000000LL) { *p.fb_err = 1; break; }      // ~3 s: fail, do not hang
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            float *sS = sT;                                   // [0,64) scale, [64,128) shift of this CTA's channels
-            if (e < 64) {
-                const int c = ch0 + e;
-                float t0s = 0.f, t1s = 0.f;
-#pragma unroll
-                for (int k = 0; k < kBnSumCopies; ++k) { t0s += __ldcg(p.stats + (2 * k) * p.out_C + c); t1s += __ldcg(p.stats + (2 * k + 1) * p.out_C + c); }
-                const double mu = (double)t0s / (double)p.fb_count;
-                double var = (double)t1s / (double)p.fb_count - mu * mu;
-                if (var < 0.0) var = 0.0;
-                const float is = (float)(1.0 / sqrt(var + (double)p.fb_eps));
-                const float g = p.fb_gamma[c];
-                sS[e] = is * g;
-                sS[64 + e] = p.fb_beta[c] - (float)mu * is * g;
-                if (blockIdx.x == 0 && blockIdx.z == 0) {
-                    p.fb_save_mean[c] = (float)mu; p.fb_save_invstd[c] = is;
-                    if (p.fb_running_mean) {
-                        const double unbiased = p.fb_count > 1.f ? var * (double)p.fb_count / ((double)p.fb_count - 1.0) : var;
-                        p.fb_running_mean[c] = (1.f - p.fb_momentum) * p.fb_running_mean[c] + p.fb_momentum * (float)mu;
-                        p.fb_running_var[c] = (1.f - p.fb_momentum) * p.fb_running_var[c] + p.fb_momentum * (float)unbiased;
-                    }
+            epi_bar();
+            if (et == 0) {
+                const uint32_t gen = ld_acquire_gpu_u32(p.fb_sync + 1);
+                if (atomicAdd(p.fb_sync, 1u) == gridDim.x - 1) {
+                    *(volatile uint32_t *)p.fb_sync = 0u;               // self-resetting: ready for the next launch
+                    __threadfence();
+                    st_release_gpu_u32(p.fb_sync + 1, gen + 1);
+                } else {
+                    const long long t0 = clock64();
+                    while (ld_acquire_gpu_u32(p.fb_sync + 1) == gen)
+                        if (clock64() - t0 > 8000000000LL) { *p.fb_err = 1; __threadfence_system(); __trap(); }   // ~4 s: fail loudly
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            bf16 *ydst = p.fb_y + pix_off;
+            epi_bar();
+            // ---- pass 2: y = relu(bn(z) + res) over this CTA's own tiles (z re-read from L2)
+            int cur_n = -1;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile<BN_TILE>(p, t);
+                if (tc.n != cur_n) {
+                    cur_n = tc.n;
+                    epi_bar();
+                    for (int c = et; c < BN_TILE; c += 128) {
+                        const int ch = tc.ch0 + c;
+                        float t0s = 0.f, t1s = 0.f;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + half * 32, v);
-                tmem_ld_wait();
+                        for (int k = 0; k < kBnSumCopies; ++k) { t0s += __ldcg(p.stats + (2 * k) * p.out_C + ch); t1s += __ldcg(p.stats + (2 * k + 1) * p.out_C + ch); }
+                        const double mean_d = (double)t0s / (double)p.fb_count;
+                        double var_d = (double)t1s / (double)p.fb_count - mean_d * mean_d;
+                        if (var_d < 0.0) var_d = 0.0;
+                        const float mean = (float)mean_d, var = (float)var_d;
+                        const float istd = (float)(1.0 / sqrt(var_d + (double)p.fb_eps));
+                        const float g = p.fb_gamma[ch];
+                        sSS[c] = istd * g;
+                        sSS[BN_TILE + c] = fmaf(-mean, istd * g, p.fb_beta[ch]);
+                        if (tc.m == 0 && tc.z == 0) {                 // exactly one tile per channel block records the statistics
+                            p.fb_save_mean[ch] = mean; p.fb_save_invstd[ch] = istd;
+                            if (p.fb_running_mean) {
+                                const float unbiased = p.fb_count > 1.f ? var * p.fb_count / (p.fb_count - 1.f) : var;
+                                p.fb_running_mean[ch] = (1.f - p.fb_momentum) * p.fb_running_mean[ch] + p.fb_momentum * mean;
+                                p.fb_running_var[ch] = (1.f - p.fb_momentum) * p.fb_running_var[ch] + p.fb_momentum * unbiased;
+                            }
+                        }
+                    }
+                    epi_bar();
+                }
+                float sc[8], sh[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int col = half * 32 + j * 8;
+                for (int e = 0; e < 8; ++e) { sc[e] = sSS[chunk * 8 + e]; sh[e] = sSS[BN_TILE + chunk * 8 + e]; }
+#pragma unroll 4
+                for (int i = 0; i < CPR; ++i) {
+                    const int row = rsub + i * (128 / CPR);
+                    const int w_l = row & (p.BW - 1);
+                    const int tt = row >> p.lgBW;
+                    const int h_l = tt & (p.BH - 1), n_l = tt >> p.lgBH;
+                    const int64_t off = (((int64_t)(tc.n_blk * p.BN + n_l) * p.out_H + (tc.h_blk * p.BH + h_l)) * p.out_W + w_l) * p.out_C + tc.ch0 + chunk * 8;
+                    const uint4 zr = __ldcg((const uint4 *)(p.out + off));
                     uint4 rr = make_uint4(0, 0, 0, 0);
-                    if (p.fb_res) rr = *(const uint4 *)(p.fb_res + pix_off + col);
-                    const __nv_bfloat162 *r2 = (const __nv_bfloat162 *)&rr;
+                    if (p.fb_res) rr = *(const uint4 *)(p.fb_res + off);
+                    const __nv_bfloat162 *z2 = (const __nv_bfloat162 *)&zr, *r2 = (const __nv_bfloat162 *)&rr;
                     uint4 pk;
                     __nv_bfloat162 *p2 = (__nv_bfloat162 *)&pk;
 #pragma unroll
-                    for (int k2 = 0; k2 < 4; ++k2) {
-                        // normalise the bf16-rounded conv output (what is stored and what backward reads)
-                        float2 xr = __bfloat1622float2(__floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2 * k2]), __uint_as_float(v[j * 8 + 2 * k2 + 1])));
-                        float a = fmaf(xr.x, sS[col + 2 * k2], sS[64 + col + 2 * k2]);
-                        float b = fmaf(xr.y, sS[col + 2 * k2 + 1], sS[64 + col + 2 * k2 + 1]);
-                        if (p.fb_res) { float2 rf = __bfloat1622float2(r2[k2]); a += rf.x; b += rf.y; }
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 zf = __bfloat1622float2(z2[e]);
+                        float a = fmaf(zf.x, sc[2 * e], sh[2 * e]), b = fmaf(zf.y, sc[2 * e + 1], sh[2 * e + 1]);
+                        if (p.fb_res) { const float2 rf = __bfloat1622float2(r2[e]); a += rf.x; b += rf.y; }
                         if (p.fb_relu) { a = a > 0.f ? a : 0.f; b = b > 0.f ? b : 0.f; }
-                        p2[k2] = __floats2bfloat162_rn(a, b);
+                        p2[e] = __floats2bfloat162_rn(a, b);
                     }
-                    *(uint4 *)(ydst + col) = pk;
+                    *(uint4 *)(p.fb_y + off) = pk;
                 }
             }
         }
-        }   // !(SPLIT && crank == 1)
         tc_fence_before();
     }
-    if (SPLIT && warp < 2) { cluster_arrive(); cluster_wait(); }      // every thread of both CTAs joins the barrier once
     __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
 }
 
 // =================================================================================
@@ -363,8 +450,9 @@ constexpr int kStagesWg = 3;
 constexpr int kBoxBytes = 128 * 128;         // [128 pixel rows][64 bf16]
 constexpr int kWgStageBytes = 4 * kBoxBytes; // up to 2 dY boxes + 2 X boxes
 constexpr int kWgSmem = kStagesWg * kWgStageBytes + 1024 + 256;
+constexpr int kWgThreads = 224;              // warps: 0 dY-TMA, 1 MMA, 2..5 epilogue, 6 X-TMA
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kWgThreads, 1)
 k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap dy_map,
         const __grid_constant__ WgradParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -385,7 +473,7 @@ k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUten
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&x_map); prefetch_tmap(&dy_map);
-        for (int i = 0; i < kStagesWg; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kStagesWg; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
@@ -398,6 +486,20 @@ k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUten
     pdl_wait();
 
     if (warp == 0) {
+        // ---- TMA producer: dY boxes (the two producers' streams overlap in the TMA unit)
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int pt = pt0; pt < pt1; ++pt) {
+                uint8_t *st = smem + stage * kWgStageBytes;
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&full[stage], mb * kBoxBytes);
+                for (int j = 0; j < mb; ++j)
+                    tma_load_2d(st + j * kBoxBytes, &dy_map, &full[stage], co0 + j * 64, pt * 128);
+                if (++stage == kStagesWg) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 6) {
+        // ---- TMA producer: shifted input boxes
         if (lane == 0) {
             int tap[2], cc[2];
             for (int j = 0; j < nb; ++j) { int c = chunk0 + j; tap[j] = c / p.c_chunks; cc[j] = c - tap[j] * p.c_chunks; }
@@ -406,9 +508,7 @@ k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUten
                 const int n_blk = pt / p.h_blocks, h_blk = pt - n_blk * p.h_blocks;
                 uint8_t *st = smem + stage * kWgStageBytes;
                 mbar_wait(&empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full[stage], (mb + nb) * kBoxBytes);
-                for (int j = 0; j < mb; ++j)
-                    tma_load_2d(st + j * kBoxBytes, &dy_map, &full[stage], co0 + j * 64, pt * 128);
+                mbar_arrive_expect_tx(&full[stage], nb * kBoxBytes);
                 for (int j = 0; j < nb; ++j)
                     tma_load_4d(st + (2 + j) * kBoxBytes, &x_map, &full[stage], cc[j] * 64, p.dw[tap[j]],
                                 h_blk * p.BH * p.a_hstep + p.dh[tap[j]], n_blk * p.BN);
@@ -441,7 +541,7 @@ k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUten
         else { row = q * 16 + lane; valid = lane < 16; }
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        float *dst_row = p.out + ((int64_t)blockIdx.z * p.Co + co0 + row) * p.out_pitch;
+        float *dst_row = p.out + ((int64_t)(p.atomic ? 0 : blockIdx.z) * p.Co + co0 + row) * p.out_pitch;
         uint32_t v[32];
         for (int j = 0; j < nb; ++j) {
             const int c = chunk0 + j;
@@ -453,10 +553,17 @@ k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUten
                 tmem_ld_wait();
                 if (valid) {
                     float4 *d4 = (float4 *)(dst + half * 32);
+                    if (p.atomic) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        d4[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]),
-                                            __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]));
+                        for (int e = 0; e < 8; ++e)
+                            red_add_f4((float *)(d4 + e), __uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]),
+                                       __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            d4[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]),
+                                                __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]));
+                    }
                 }
             }
         }
@@ -471,16 +578,31 @@ k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUten
 // =================================================================================
 static std::once_flag g_attr_once;
 static void set_attrs() {
-    cudaFuncSetAttribute(k_tapgemm<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tap_smem(4));
-    cudaFuncSetAttribute(k_tapgemm<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tap_smem(8));
-    cudaFuncSetAttribute(k_tapgemm<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tap_smem(6, true));
+    cudaFuncSetAttribute(k_conv<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmem);
+    cudaFuncSetAttribute(k_conv<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmem);
     cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
+}
+
+// Output-channel tile: 128 when the 64-wide tiling would need more than one wave of CTAs (halves the
+// activation re-reads and doubles the FLOPs per TMA byte); 64 otherwise (more CTAs, shorter epilogues).
+static int pick_bn_tile(int64_t m_tiles, int channels, int classes) {
+    if (channels % 128 != 0) return 64;
+    return m_tiles * (channels / 64) * classes > (int64_t)umma_num_sms() ? 128 : 64;
+}
+
+static void finish_plan(UmmaConvPlan *plan, int64_t m_tiles, int channels) {
+    ConvParams &p = plan->p;
+    p.lgBW = ilog2(p.BW); p.lgBH = ilog2(p.BH);
+    p.m_tiles = (int)m_tiles; p.n_tiles = channels / plan->bn_tile;
+    p.total_tiles = p.m_tiles * p.n_tiles * p.nclasses;
+    plan->grid = std::min(p.total_tiles, umma_num_sms());
 }
 
 int umma_plan_fprop(const ConvGeom &g, const bf16 *x, const bf16 *w, bf16 *y, UmmaConvPlan *plan) {
     plan->valid = false;
     B2_CHECK(umma_conv_eligible(g), B2_ERR_UNSUPPORTED, "umma fprop: shape not eligible");
-    TapGemmParams &p = plan->p;
+    B2_TRY(umma_init());
+    ConvParams &p = plan->p;
     memset(&p, 0, sizeof(p));
     B2_CHECK(tile_geometry(g.N, g.Ho, g.Wo, &p.BW, &p.BH, &p.BN), B2_ERR_UNSUPPORTED, "umma fprop: tile geometry");
     p.h_blocks = g.Ho / p.BH; p.a_hstep = g.stride; p.c_chunks = g.Ci / 64;
@@ -494,9 +616,11 @@ int umma_plan_fprop(const ConvGeom &g, const bf16 *x, const bf16 *w, bf16 *y, Um
             if (!tap_alive(dh, g.stride, g.Ho, g.Hi) || !tap_alive(dw, g.stride, g.Wo, g.Wi)) continue;
             c.dh[c.ntaps] = dh; c.dw[c.ntaps] = dw; c.kofs[c.ntaps] = (kh * g.kw + kw) * g.Ci; ++c.ntaps;
         }
+    const int64_t m_tiles = (int64_t)(g.N / p.BN) * p.h_blocks;
+    plan->bn_tile = pick_bn_tile(m_tiles, g.Co, 1);
     B2_TRY(make_map_nhwc(&plan->a_map, x, g.N, g.Hi, g.Wi, g.Ci, p.BW, p.BH, p.BN, g.stride));
-    B2_TRY(make_map_2d(&plan->b_map, w, g.Co, (int64_t)g.kh * g.kw * g.Ci, 64));
-    plan->grid = dim3((unsigned)(g.N / p.BN * p.h_blocks), (unsigned)(g.Co / 64), 1);
+    B2_TRY(make_map_2d(&plan->b_map, w, g.Co, (int64_t)g.kh * g.kw * g.Ci, plan->bn_tile));
+    finish_plan(plan, m_tiles, g.Co);
     plan->flops = 2.0 * g.M() * g.Co * (double)c.ntaps * g.Ci;
     plan->valid = true;
     return 0;
@@ -505,7 +629,8 @@ int umma_plan_fprop(const ConvGeom &g, const bf16 *x, const bf16 *w, bf16 *y, Um
 int umma_plan_dgrad(const ConvGeom &g, const bf16 *dy, const bf16 *w, bf16 *dx, bool acc, UmmaConvPlan *plan) {
     plan->valid = false;
     B2_CHECK(umma_conv_eligible(g), B2_ERR_UNSUPPORTED, "umma dgrad: shape not eligible");
-    TapGemmParams &p = plan->p;
+    B2_TRY(umma_init());
+    ConvParams &p = plan->p;
     memset(&p, 0, sizeof(p));
     // box space = dY's pixel grid for stride 2 (one class per output parity), dX's grid for stride 1
     B2_CHECK(tile_geometry(g.N, g.Ho, g.Wo, &p.BW, &p.BH, &p.BN), B2_ERR_UNSUPPORTED, "umma dgrad: tile geometry");
@@ -532,32 +657,31 @@ int umma_plan_dgrad(const ConvGeom &g, const bf16 *dy, const bf16 *w, bf16 *dx, 
             if (c.ntaps > 0) ++p.nclasses;      // a class without taps contributes nothing
             else B2_CHECK(acc || s == 1, B2_ERR_UNSUPPORTED, "umma dgrad: empty parity class needs acc (caller zero-fills)");
         }
+    const int64_t m_tiles = (int64_t)(g.N / p.BN) * p.h_blocks;
+    plan->bn_tile = pick_bn_tile(m_tiles, g.Ci, p.nclasses);
     B2_TRY(make_map_nhwc(&plan->a_map, dy, g.N, g.Ho, g.Wo, g.Co, p.BW, p.BH, p.BN, 1));
     B2_TRY(make_map_2d(&plan->b_map, w, g.Co, (int64_t)g.kh * g.kw * g.Ci, 64));
-    plan->grid = dim3((unsigned)(g.N / p.BN * p.h_blocks), (unsigned)(g.Ci / 64), (unsigned)p.nclasses);
+    finish_plan(plan, m_tiles, g.Ci);
     plan->flops = 2.0 * (double)g.N * g.Ho * g.Wo * g.Ci * taps_total * g.Co;
     plan->valid = true;
+    return 0;
+}
+
+int umma_conv_check_coresident(const UmmaConvPlan &plan) {
+    std::call_once(g_attr_once, set_attrs);
+    int per_sm = 0;
+    if (plan.bn_tile == 128) B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_conv<128>, kConvThreads, ConvCfg<128>::kSmem));
+    else B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_conv<64>, kConvThreads, ConvCfg<64>::kSmem));
+    B2_CHECK(per_sm >= 1 && plan.grid <= per_sm * umma_num_sms(), B2_ERR_UNSUPPORTED,
+             "fused conv+BatchNorm: grid of %d CTAs is not co-resident (%d per SM x %d SMs)", plan.grid, per_sm, umma_num_sms());
     return 0;
 }
 
 int umma_conv_launch(const UmmaConvPlan &plan, cudaStream_t s) {
     B2_CHECK(plan.valid, B2_ERR_STATE, "umma conv: plan not valid");
     std::call_once(g_attr_once, set_attrs);
-    const unsigned ctas = plan.grid.x * plan.grid.y * plan.grid.z;
-    int min_ksteps = 1 << 30;
-    for (int c = 0; c < plan.p.nclasses; ++c) min_ksteps = std::min(min_ksteps, plan.p.cls[c].ntaps * plan.p.c_chunks);
-    // measured (r01): parity-green but 4% slower end to end (1.051 vs 1.007 ms/step) -- the extra
-    // cluster barrier / DSMEM hand-off and the competition with the concurrent wgrad stream outweigh
-    // the additional SMs.  Kept behind B2_SPLITK=1 for layer-level experiments.
-    static const bool allow_split = [] { const char *e = getenv("B2_SPLITK"); return e && e[0] == '1'; }();
-    if (allow_split && ctas <= (unsigned)kNumSMs && min_ksteps >= 4) {
-        // split-K cluster pair: twice the CTAs (and SMs) per output tile
-        dim3 g(plan.grid.x * 2, plan.grid.y, plan.grid.z);
-        cudaError_t e = launch_kernel_cluster(k_tapgemm<6, true>, g, dim3(192), (size_t)tap_smem(6, true), s, 2u, plan.a_map, plan.b_map, plan.p);
-        ++g_launches;
-        B2_CHECK(e == cudaSuccess, B2_ERR_CUDA, "k_tapgemm<split> launch failed: %s", cudaGetErrorString(e));
-    } else if (ctas <= (unsigned)kNumSMs) { B2_LAUNCH((k_tapgemm<8, false>), plan.grid, 192, tap_smem(8), s, plan.a_map, plan.b_map, plan.p); }
-    else { B2_LAUNCH((k_tapgemm<4, false>), plan.grid, 192, tap_smem(4), s, plan.a_map, plan.b_map, plan.p); }
+    if (plan.bn_tile == 128) { B2_LAUNCH((k_conv<128>), plan.grid, kConvThreads, ConvCfg<128>::kSmem, s, plan.a_map, plan.b_map, plan.p); }
+    else { B2_LAUNCH((k_conv<64>), plan.grid, kConvThreads, ConvCfg<64>::kSmem, s, plan.a_map, plan.b_map, plan.p); }
     return 0;
 }
 
@@ -587,7 +711,7 @@ size_t umma_wgrad_workspace(const ConvGeom &g) {
 }
 
 int umma_plan_wgrad(const ConvGeom &g, const bf16 *x, const bf16 *dy, float *dw, float *partial, size_t partial_floats,
-                    UmmaWgradPlan *plan) {
+                    bool deterministic, UmmaWgradPlan *plan) {
     plan->valid = false;
     B2_CHECK(umma_conv_eligible(g), B2_ERR_UNSUPPORTED, "umma wgrad: shape not eligible");
     WgradParams &p = plan->p;
@@ -604,10 +728,10 @@ int umma_plan_wgrad(const ConvGeom &g, const bf16 *x, const bf16 *dy, float *dw,
             }
     plan->need_zero = n < g.kh * g.kw;
     plan->dw = dw;
-    if (p.splits > 1) {
+    if (p.splits > 1 && deterministic) {
         B2_CHECK((size_t)p.splits * g.Co * n * g.Ci <= partial_floats, B2_ERR_ARG, "umma wgrad: workspace too small");
-        p.out = partial; p.out_pitch = n * g.Ci; p.compact = 1;
-    } else { p.out = dw; p.out_pitch = g.K(); p.compact = 0; }
+        p.out = partial; p.out_pitch = n * g.Ci; p.compact = 1; p.atomic = 0;
+    } else { p.out = dw; p.out_pitch = g.K(); p.compact = 0; p.atomic = p.splits > 1 ? 1 : 0; }
     B2_TRY(make_map_nhwc(&plan->x_map, x, g.N, g.Hi, g.Wi, g.Ci, p.BW, p.BH, p.BN, g.stride));
     B2_TRY(make_map_2d(&plan->dy_map, dy, g.M(), g.Co, 128));
     plan->grid = dim3((unsigned)kt, (unsigned)(g.Co / (64 * p.m_boxes)), (unsigned)p.splits);
@@ -644,8 +768,8 @@ int umma_wgrad_launch(const UmmaWgradPlan &plan, cudaStream_t s) {
     B2_CHECK(plan.valid, B2_ERR_STATE, "umma wgrad: plan not valid");
     std::call_once(g_attr_once, set_attrs);
     const WgradParams &p = plan.p;
-    B2_LAUNCH(k_wgrad, plan.grid, 192, kWgSmem, s, plan.x_map, plan.dy_map, plan.p);
-    if (p.splits > 1) {
+    B2_LAUNCH(k_wgrad, plan.grid, kWgThreads, kWgSmem, s, plan.x_map, plan.dy_map, plan.p);
+    if (p.splits > 1 && !p.atomic) {
         int64_t n4 = (int64_t)p.Co * p.out_pitch / 4;
         int blocks = (int)ceil_div(n4, 256); if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
         B2_LAUNCH(k_wgrad_reduce, blocks, 256, 0, s, p.out, plan.dw, p);

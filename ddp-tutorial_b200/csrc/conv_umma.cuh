@@ -16,11 +16,13 @@ struct TapClass {
     int kofs[kMaxTaps];         // element offset of the tap's 64-wide K slices in the B matrix
 };
 
-struct TapGemmParams {
+// Parameters of the persistent fprop / dgrad kernel k_conv<BN_TILE> (conv_umma.cu).
+struct ConvParams {
     int nclasses;
     TapClass cls[4];
     int c_chunks;               // source channels / 64
-    int BW, BH, BN, h_blocks;   // 128-pixel tile = BN images x BH rows x BW cols (box space)
+    int BW, BH, BN, h_blocks;   // 128-pixel tile = BN images x BH rows x BW cols (box space), all powers of two
+    int lgBW, lgBH;
     int a_hstep;                // source rows per box row (conv stride for fprop, else 1)
     int out_H, out_W, out_C, os;
     bf16 *out;
@@ -28,6 +30,7 @@ struct TapGemmParams {
     int b_mn;                   // 0: B tile rows = output channel, cols = K (fprop)
                                 // 1: B tile rows = K (co), cols = output channel (dgrad reads the
                                 //    same [Co][taps*Ci] weight copy as an MN-major operand)
+    int m_tiles, n_tiles, total_tiles;   // tile t = (class * n_tiles + n) * m_tiles + m ; CTA b runs t = b, b + grid, ...
     float *stats;               // optional [copies][2][out_C] per-channel sum / sum of squares (atomics); may be null
     // optional (dgrad that produces the FINAL gradient of a fused BatchNorm's output tensor): also
     // accumulate that BatchNorm's backward sums  sum(g), sum(g*xhat),  g = dY * [y > 0]
@@ -35,23 +38,25 @@ struct TapGemmParams {
     const bf16 *bn_x, *bn_y;    // the BatchNorm's input / output (same NHWC shape as `out`)
     const float *bn_mean, *bn_invstd;
     int bn_relu;
-    // optional (fprop whose whole grid is co-resident): apply the consumer BatchNorm (+residual, ReLU)
-    // in this kernel.  After a CTA has added its tile's sums to `stats` it joins a grid-wide counter
-    // barrier; the fp32 accumulators stay in TMEM across the barrier and are then normalised and
-    // written as the BatchNorm output `fb_y` (the raw conv output `out` is still stored: backward
-    // needs it).  One launch replaces conv + BN-apply.
+    // optional (fprop): apply the consumer BatchNorm (+residual, ReLU) in this kernel.  After a CTA has
+    // stored its tiles (bf16 conv output `out`, which backward needs anyway) and added their per-channel
+    // sums to `stats`, it joins a grid-wide barrier (the grid is persistent: at most one CTA per SM, all
+    // co-resident) and then normalises its own tiles -- re-read from L2 -- into the BatchNorm output `fb_y`.
+    // One launch replaces conv + BN-statistics + BN-apply.
     int fuse_bn;
     bf16 *fb_y; const bf16 *fb_res;
     const float *fb_gamma, *fb_beta;
     float *fb_save_mean, *fb_save_invstd, *fb_running_mean, *fb_running_var;
-    unsigned int *fb_counter; int *fb_err;
+    unsigned int *fb_sync;      // [0] arrival counter, [1] generation (self-resetting sense barrier)
+    int *fb_err;
     float fb_count, fb_eps, fb_momentum; int fb_relu;
 };
 
 struct UmmaConvPlan {
     CUtensorMap a_map, b_map;
-    TapGemmParams p;
-    dim3 grid;
+    ConvParams p;
+    int bn_tile;                // 64 or 128 output channels per tile
+    int grid;                   // persistent CTAs (<= SM count)
     double flops;               // executed FLOPs (dead taps skipped)
     bool valid;
 };
@@ -64,9 +69,10 @@ struct WgradParams {
     int BW, BH, BN, h_blocks, a_hstep;
     int pix_tiles, tiles_per_split, splits;
     int m_boxes;                // Co tile = 64*m_boxes (1 or 2)
-    float *out;                 // dW (splits == 1) or compact partials [splits][Co][alive taps*Ci]
+    float *out;                 // dW (atomic / single-split mode) or compact partials [splits][Co][alive taps*Ci]
     int out_pitch;              // row pitch of `out` in floats
     int compact;                // 1: columns are (alive tap, ci); 0: columns are (tap id, ci) as in dW
+    int atomic;                 // 1: red.global.add straight into dW (dW zeroed once per step by the caller)
 };
 
 struct UmmaWgradPlan {
@@ -81,12 +87,17 @@ struct UmmaWgradPlan {
 
 bool umma_conv_eligible(const ConvGeom &g);
 int umma_init();   // resolves the driver entry point for tensor-map encoding
+int umma_num_sms();
 int umma_plan_fprop(const ConvGeom &g, const bf16 *x, const bf16 *w, bf16 *y, UmmaConvPlan *plan);
 int umma_plan_dgrad(const ConvGeom &g, const bf16 *dy, const bf16 *w, bf16 *dx, bool acc, UmmaConvPlan *plan);
+// checks (once per plan) that the persistent grid is co-resident; required before enabling fuse_bn
+int umma_conv_check_coresident(const UmmaConvPlan &plan);
 int umma_conv_launch(const UmmaConvPlan &plan, cudaStream_t s);
+// deterministic: split-K partials + a reduce kernel (fixed summation order); otherwise the splits add
+// into dW with red.global.add (dW must have been zeroed: umma_wgrad_needs_zero()).
 size_t umma_wgrad_workspace(const ConvGeom &g);
 int umma_plan_wgrad(const ConvGeom &g, const bf16 *x, const bf16 *dy, float *dw, float *partial, size_t partial_floats,
-                    UmmaWgradPlan *plan);
+                    bool deterministic, UmmaWgradPlan *plan);
 int umma_wgrad_launch(const UmmaWgradPlan &plan, cudaStream_t s);
 // zero the dW columns of taps that never touch the input (call once; they are never written)
 int umma_wgrad_zero_dead(const UmmaWgradPlan &plan, cudaStream_t s);

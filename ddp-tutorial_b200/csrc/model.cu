@@ -403,10 +403,18 @@ int Model::time_conv_kernels(int iters, double ms[3], double flops[3], int launc
     for (int i = 0; i < 3; ++i) { ms[i] = 0; flops[i] = 0; launches[i] = 0; }
     cudaEvent_t a, b;
     B2_CUDA(cudaEventCreate(&a)); B2_CUDA(cudaEventCreate(&b));
+    // every launch starts from zeroed BatchNorm sums (as in a real step: the fused conv+BN kernels then pay
+    // their grid barrier and normalise real statistics) and from zeroed gradients (atomic split-K weight
+    // gradients); the memsets are part of the timed region.  Running statistics are saved and restored.
+    float *saved_buffers = nullptr;
+    if (p_buffers && n_buffers) {
+        B2_CUDA(cudaMalloc(&saved_buffers, (size_t)n_buffers * 4));
+        B2_CUDA(cudaMemcpyAsync(saved_buffers, p_buffers, (size_t)n_buffers * 4, cudaMemcpyDeviceToDevice, s));
+    }
     auto timed = [&](int cls, double fl, auto &&launch) -> int {
-        for (int w = 0; w < 2; ++w) B2_TRY(launch());
+        for (int w = 0; w < 2; ++w) { if (bn_sums_bytes) B2_CUDA(cudaMemsetAsync(bn_sums, 0, bn_sums_bytes, s)); B2_TRY(launch()); }
         B2_CUDA(cudaEventRecord(a, s));
-        for (int it = 0; it < iters; ++it) B2_TRY(launch());
+        for (int it = 0; it < iters; ++it) { if (bn_sums_bytes) B2_CUDA(cudaMemsetAsync(bn_sums, 0, bn_sums_bytes, s)); B2_TRY(launch()); }
         B2_CUDA(cudaEventRecord(b, s));
         B2_CUDA(cudaEventSynchronize(b));
         float t = 0.f;
@@ -419,6 +427,11 @@ int Model::time_conv_kernels(int iters, double ms[3], double flops[3], int launc
         B2_TRY(timed(0, o.fplan.flops, [&] { return umma_conv_launch(o.fplan, s); }));
         if (o.use_umma && o.need_dgrad) B2_TRY(timed(1, o.dplan.flops, [&] { return umma_conv_launch(o.dplan, s); }));
         B2_TRY(timed(2, o.wplan.flops, [&] { return umma_wgrad_launch(o.wplan, s); }));
+    }
+    if (saved_buffers) {
+        B2_CUDA(cudaMemcpyAsync(p_buffers, saved_buffers, (size_t)n_buffers * 4, cudaMemcpyDeviceToDevice, s));
+        B2_CUDA(cudaStreamSynchronize(s));
+        cudaFree(saved_buffers);
     }
     cudaEventDestroy(a); cudaEventDestroy(b);
     return 0;
@@ -435,11 +448,13 @@ int Model::sync_weights(cudaStream_t s) {
 }
 
 int Model::build_plans() {
+    zero_grads_each_step = false;
     for (Op &o : ops) {
         if (o.type == OP_CONV && o.stem_umma) {
             Tensor &to = tensors[o.out];
             B2_TRY(umma_plan_fprop(o.vg, o.col, o.wpad, (bf16 *)to.val, &o.fplan));
-            B2_TRY(umma_plan_wgrad(o.vg, o.col, (const bf16 *)to.grad, o.dwpad, wgrad_ws, wgrad_floats, &o.wplan));
+            B2_TRY(umma_plan_wgrad(o.vg, o.col, (const bf16 *)to.grad, o.dwpad, wgrad_ws, wgrad_floats, deterministic, &o.wplan));
+            if (o.wplan.p.atomic) zero_grads_each_step = true;
             continue;
         }
         if (o.type != OP_CONV || !o.use_umma) continue;
@@ -451,7 +466,8 @@ int Model::build_plans() {
             bool sparse = o.g.stride == 2 && o.g.kh == 1;
             B2_TRY(umma_plan_dgrad(o.g, (const bf16 *)to.grad, wb, (bf16 *)ti.grad, o.acc_in || sparse, &o.dplan));
         }
-        B2_TRY(umma_plan_wgrad(o.g, (const bf16 *)ti.val, (const bf16 *)to.grad, p_grads + o.w_off, wgrad_ws, wgrad_floats, &o.wplan));
+        B2_TRY(umma_plan_wgrad(o.g, (const bf16 *)ti.val, (const bf16 *)to.grad, p_grads + o.w_off, wgrad_ws, wgrad_floats, deterministic, &o.wplan));
+        if (o.wplan.p.atomic) zero_grads_each_step = true;
         B2_TRY(umma_wgrad_zero_dead(o.wplan, 0));      // once: dead-tap gradients are exactly zero and never rewritten
     }
     B2_CUDA(cudaStreamSynchronize(0));
@@ -461,11 +477,11 @@ int Model::build_plans() {
         static const bool allow_fb = [] { const char *e = getenv("B2_FUSE_BN_FWD"); return !(e && e[0] == '0'); }();
         for (Op &c : ops)
             if (c.type == OP_CONV && c.out == b.in) {
-                TapGemmParams &q = c.fplan.p;
+                ConvParams &q = c.fplan.p;
                 q.stats = b.fsum;
-                const unsigned ctas = c.fplan.grid.x * c.fplan.grid.y * c.fplan.grid.z;
-                // conv + BatchNorm(+residual, ReLU) in one launch when the whole grid is co-resident
-                if (allow_fb && c.use_umma && ctas <= 2u * kNumSMs) {
+                // conv + BatchNorm(+residual, ReLU) in one launch: the kernel is persistent (grid <= #SMs), so its
+                // grid barrier only needs one CTA per SM to be resident -- verified with the occupancy API
+                if (allow_fb && umma_conv_check_coresident(c.fplan) == 0) {
                     const Tensor &tx = tensors[b.in];
                     q.fuse_bn = 1;
                     q.fb_y = (bf16 *)tensors[b.out].val;
@@ -474,7 +490,7 @@ int Model::build_plans() {
                     q.fb_save_mean = b.bn.mean; q.fb_save_invstd = b.bn.invstd;
                     q.fb_running_mean = p_buffers ? p_buffers + b.rm_off : nullptr;
                     q.fb_running_var = p_buffers ? p_buffers + b.rv_off : nullptr;
-                    q.fb_counter = b.fb_counter; q.fb_err = fb_err;
+                    q.fb_sync = b.fb_counter; q.fb_err = fb_err;
                     q.fb_count = (float)((int64_t)tx.N * tx.H * tx.W); q.fb_eps = 1e-5f; q.fb_momentum = 0.1f;
                     q.fb_relu = b.relu ? 1 : 0;
                     b.fwd_in_conv = true;
@@ -486,12 +502,11 @@ int Model::build_plans() {
             bool consumes = (c.in == b.out) || (c.res == b.out);
             if (!consumes) continue;
             bool covers_all = c.g.stride == 1 || c.g.kh >= c.g.stride;      // a 1x1 stride-2 dgrad only touches even pixels
-            // measured (r01): the fused epilogue's per-row x/y gathers cost more than the separate
-            // coalesced reduce pass saves (1.055 vs 1.010 ms/step) -> off until the epilogue is
-            // re-tiled for row-coalesced access (env B2_FUSE_BN_BWD=1 enables it for experiments)
-            static const bool enable = [] { const char *e = getenv("B2_FUSE_BN_BWD"); return e && e[0] == '1'; }();
+            // the dgrad that finalises d(b.out) reads x / y row-coalesced in its staged epilogue and adds the
+            // BatchNorm-backward sums there: no separate reduce pass over (x, y, dy)  (B2_FUSE_BN_BWD=0 disables)
+            static const bool enable = [] { const char *e = getenv("B2_FUSE_BN_BWD"); return !(e && e[0] == '0'); }();
             if (enable && c.type == OP_CONV && c.use_umma && c.need_dgrad && c.in == b.out && covers_all) {
-                TapGemmParams &q = c.dplan.p;
+                ConvParams &q = c.dplan.p;
                 q.bn_bsum = b.bsum; q.bn_x = (const bf16 *)tensors[b.in].val; q.bn_y = (const bf16 *)tensors[b.out].val;
                 q.bn_mean = b.bn.mean; q.bn_invstd = b.bn.invstd; q.bn_relu = b.relu ? 1 : 0;
                 b.bwd_sums_fused = true;
@@ -558,6 +573,27 @@ int Model::forward(const float *x_nchw, float *logits, cudaStream_t s) {
 int Model::forward_impl(const float *x_nchw, float *logits, cudaStream_t s) {
     cur_x = x_nchw;
     if (bn_sums_bytes) B2_CUDA(cudaMemsetAsync(bn_sums, 0, bn_sums_bytes, s));
+    // split-K weight gradients accumulate with red.global.add: the flat gradient vector must be zero when
+    // backward starts.  The previous step's optimizer has consumed it (stream order), so zero it now on the
+    // weight-gradient stream, under the forward pass (joined before forward returns: graph-capturable).
+    const bool zero_side = zero_grads_each_step && wgrad_async && !profiling;
+    if (zero_grads_each_step) {
+        if (zero_side) {
+            B2_TRY(ensure_side_streams());
+            B2_CUDA(cudaEventRecord(wg_fork, s));
+            B2_CUDA(cudaStreamWaitEvent(wg_stream, wg_fork, 0));
+            B2_CUDA(cudaMemsetAsync(p_grads, 0, (size_t)n_params * 4, wg_stream));
+            for (Op &o : ops)        // the stem accumulates into its own padded dW buffer
+                if (o.type == OP_CONV && o.stem_umma && o.wplan.p.atomic)
+                    B2_CUDA(cudaMemsetAsync(o.dwpad, 0, (size_t)o.vg.Co * o.kpad * 4, wg_stream));
+            B2_CUDA(cudaEventRecord(wg_join, wg_stream));
+        } else {
+            B2_CUDA(cudaMemsetAsync(p_grads, 0, (size_t)n_params * 4, s));
+            for (Op &o : ops)
+                if (o.type == OP_CONV && o.stem_umma && o.wplan.p.atomic)
+                    B2_CUDA(cudaMemsetAsync(o.dwpad, 0, (size_t)o.vg.Co * o.kpad * 4, s));
+        }
+    }
 
     for (Op &o : ops) {
         Tensor &to = tensors[o.out];
@@ -636,6 +672,7 @@ int Model::forward_impl(const float *x_nchw, float *logits, cudaStream_t s) {
         }
         }
     }
+    if (zero_side) B2_CUDA(cudaStreamWaitEvent(s, wg_join, 0));
     return 0;
 }
 
@@ -647,17 +684,22 @@ int Model::backward(const float *dlogits, cudaStream_t s) {
     return backward_impl(dlogits, s);
 }
 
+int Model::ensure_side_streams() {
+    if (!wg_stream) {
+        B2_CUDA(cudaStreamCreateWithFlags(&wg_stream, cudaStreamNonBlocking));
+        B2_CUDA(cudaEventCreateWithFlags(&wg_fork, cudaEventDisableTiming));
+        B2_CUDA(cudaEventCreateWithFlags(&wg_join, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
 int Model::backward_impl(const float *dlogits, cudaStream_t s) {
     Tensor &tl = tensors[logits_tensor];
     B2_CUDA(cudaMemcpyAsync(tl.grad, dlogits, tl.numel * 4, cudaMemcpyDeviceToDevice, s));
     size_t next_bucket = 0;
     bool forked = false, wg_used = false;
     const bool async_wg = wgrad_async && !profiling;
-    if (async_wg && !wg_stream) {
-        B2_CUDA(cudaStreamCreateWithFlags(&wg_stream, cudaStreamNonBlocking));
-        B2_CUDA(cudaEventCreateWithFlags(&wg_fork, cudaEventDisableTiming));
-        B2_CUDA(cudaEventCreateWithFlags(&wg_join, cudaEventDisableTiming));
-    }
+    if (async_wg) B2_TRY(ensure_side_streams());
     // stream for this op's weight-gradient kernels: forks from `s` at the call (dY is final there)
     auto wgrad_stream = [&]() -> cudaStream_t {
         if (!async_wg) return s;
@@ -715,8 +757,7 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
             const double cflops = 2.0 * o.g.M() * o.g.Co * o.g.K();
             const double cbytes = ti.numel * (double)dt_size(ti.dt) + to.numel * (double)dt_size(to.dt);
             int ph = prof_begin(PC_CONV_WGRAD, o.use_umma ? o.wplan.flops : cflops, cbytes + (double)o.g.Co * o.g.K() * 4, s);
-            static const bool dbg_skip_wgrad = [] { const char *e = getenv("B2_DEBUG_SKIP_WGRAD"); return e && e[0] == '1'; }();
-            if (!dbg_skip_wgrad) {      // (timing experiments only: B2_DEBUG_SKIP_WGRAD=1 leaves stale weight gradients)
+            {
                 cudaStream_t ws = wgrad_stream();
                 if (o.use_umma) B2_TRY(umma_wgrad_launch(o.wplan, ws));
                 else B2_TRY(conv_simt_wgrad(o.g, ti.val, to.grad, ti.dt, p_grads + o.w_off, wgrad_ws, wgrad_floats, ws));
@@ -742,7 +783,7 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
             if (o.bn_fused)
                 B2_TRY(op_bn_backward_fused(ti.val, to.val, to.grad, ti.grad, o.res >= 0 ? tensors[o.res].grad : nullptr, ti.dt, M,
                                             ti.C, o.bsum, p_params + o.w_off, p_grads + o.w_off, p_grads + o.b_off, o.relu,
-                                            o.acc_in, o.acc_res, o.bwd_sums_fused, o.bn, s, o.fb_counter + 1, fb_err));
+                                            o.acc_in, o.acc_res, o.bwd_sums_fused, o.bn, s));
             else
             B2_TRY(op_bn_backward(ti.val, to.val, to.grad, ti.grad, o.res >= 0 ? tensors[o.res].grad : nullptr, ti.dt, M,
                                   ti.C, p_params + o.w_off, p_grads + o.w_off, p_grads + o.b_off, o.relu, o.acc_in,

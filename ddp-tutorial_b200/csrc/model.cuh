@@ -28,7 +28,7 @@ struct Op {
     bool bn_fused;               // statistics come from the producing conv's epilogue
     float *fsum, *bsum;          // [copies][2][C] each, inside the per-step zeroed arena
     bool fwd_in_conv;            // forward done inside the producing conv kernel (grid-barrier fusion)
-    unsigned int *fb_counter;
+    unsigned int *fb_counter;    // [0] arrivals, [1] generation of the fused conv+BN grid barrier
     bool bwd_sums_fused;         // the dgrad that finalises this BN's output gradient also accumulates bsum
     uint8_t *idx;                // maxpool argmax
     int wdt, wpitch;             // conv: weight operand type / row pitch as the kernels see it
@@ -70,6 +70,12 @@ struct Model {
     bool weights_dirty = true;
     bool plans_ready = false;
     int conv_impl = 1;           // 0 = SIMT everywhere, 1 = tcgen05 where eligible
+    // split-K weight gradients add into the flat gradient vector with red.global.add (no partials, no reduce
+    // kernel); the vector is then zeroed once per step, on the weight-gradient stream while forward runs.
+    // deterministic = true restores the fixed-order partials + reduce form (bit-reproducible run to run).
+    bool deterministic = false;
+    bool zero_grads_each_step = false;
+    int ensure_side_streams();
     int build_plans();
     // CUDA-graph replay of forward / backward (launch-latency removal): one graph per distinct
     // (input, output) pointer pair, captured on a private stream, replayed on the caller's

@@ -40,8 +40,7 @@ int op_bn_forward_fused(const void *x, void *y, const void *res, int dt, int64_t
 // sums_ready: bsum was already accumulated by the dgrad that produced dy (skip the reduce pass)
 int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx, void *dres, int dt, int64_t M, int C,
                          float *bsum, const float *gamma, float *dgamma, float *dbeta, bool relu, bool acc_dx,
-                         bool acc_dres, bool sums_ready, const BnWork &w, cudaStream_t s,
-                         unsigned int *coop_counter = nullptr, int *coop_err = nullptr);
+                         bool acc_dres, bool sums_ready, const BnWork &w, cudaStream_t s);
 
 // ---- pooling -------------------------------------------------------------------
 int op_maxpool_forward(const void *x, void *y, uint8_t *idx, int dt, int N, int Hi, int Wi, int C,

@@ -854,9 +854,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_bn_bwd_reduce_atomic(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy,
                        const float *__restrict__ mean, const float *__restrict__ invstd, bool relu, int64_t M, int C,
-                       int opb /* channel octets per block: min(C/8, 32) */, float *__restrict__ bsum,
-                       unsigned int *ticket /* zeroed per step; null = no finalize */, const float *__restrict__ gamma,
-                       float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef /* [3][C] */) {
+                       int opb /* channel octets per block: min(C/8, 32) */, float *__restrict__ bsum) {
     pdl_sync();
     // each thread owns 8 consecutive channels (16-byte loads); 256/opb row lanes per block
     const int tx = threadIdx.x % opb, ty = threadIdx.x / opb, lanes = 256 / opb;
@@ -900,27 +898,6 @@ k_bn_bwd_reduce_atomic(const T *__restrict__ x, const T *__restrict__ y, const T
             atomicAdd(dst + C + c0 + e, mine[8 + e]);
         }
     }
-    if (ticket) {
-        // the block that finishes last turns the sums into the per-channel coefficients once, so the
-        // apply kernel's blocks read 3 floats per channel instead of re-deriving them from 16 partials
-        __shared__ unsigned int s_last;
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1 ? 1u : 0u;
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            for (int c = threadIdx.x; c < C; c += blockDim.x) {
-                float sg = 0.f, sgx = 0.f;
-#pragma unroll
-                for (int k = 0; k < kBnSumCopies; ++k) { sg += __ldcg(bsum + (2 * k) * C + c); sgx += __ldcg(bsum + (2 * k + 1) * C + c); }
-                const float isc = invstd[c], muc = mean[c], a = gamma[c] * isc;
-                const float c1 = sg / (float)M, c2 = sgx / (float)M;
-                coef[c] = a; coef[C + c] = -a * c2 * isc; coef[2 * C + c] = -a * c1 + a * c2 * isc * muc;
-                dbeta[c] = sg; dgamma[c] = sgx;
-            }
-        }
-    }
 }
 
 template <typename T, int V>
@@ -928,14 +905,10 @@ __global__ void __launch_bounds__(256)
 k_bn_bwd_apply_fused(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy, T *__restrict__ dx,
                      T *__restrict__ dres, const float *__restrict__ mean, const float *__restrict__ invstd,
                      const float *__restrict__ bsum, const float *__restrict__ gamma, float *__restrict__ dgamma,
-                     float *__restrict__ dbeta, int64_t M, bool relu, bool acc_dx, bool acc_dres, int64_t total, int C,
-                     const float *__restrict__ coef_in /* [3][C] from the reduce kernel, or null */) {
+                     float *__restrict__ dbeta, int64_t M, bool relu, bool acc_dx, bool acc_dres, int64_t total, int C) {
     pdl_sync();
     extern __shared__ float sm[];     // a[C], b[C], k[C]: dx = a*g + b*x + k   (per channel)
     float *ca = sm, *cb = sm + C, *ck = sm + 2 * C;
-    if (coef_in) {
-        for (int c = threadIdx.x; c < 3 * C; c += blockDim.x) sm[c] = coef_in[c];
-    } else
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float sg = 0.f, sgx = 0.f;
 #pragma unroll
@@ -1043,174 +1016,32 @@ k_bn_bwd_small(const T *__restrict__ x, const T *__restrict__ y, const T *__rest
     }
 }
 
-// Single-pass BatchNorm backward: one block per SM keeps its share of (x, g = dy*[y>0]) in registers,
-// adds its per-channel sums, joins a grid-wide counter barrier, then applies from registers -- x, y, dy
-// are read exactly once (the two-kernel form reads them twice).  MAXI = row items per thread.
-template <int MAXI>
-__global__ void __launch_bounds__(256, 1)
-k_bn_bwd_coop(const bf16 *__restrict__ x, const bf16 *__restrict__ y, const bf16 *__restrict__ dy, bf16 *__restrict__ dx,
-              bf16 *__restrict__ dres, const float *__restrict__ mean, const float *__restrict__ invstd,
-              const float *__restrict__ gamma, float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ bsum,
-              unsigned int *counter, int *err, int64_t M, int C, int opb, bool relu, bool acc_dx, bool acc_dres) {
-    pdl_sync();
-    const int tx = threadIdx.x % opb, ty = threadIdx.x / opb, lanes = 256 / opb;
-    const int c0 = (blockIdx.x * opb + tx) * 8;
-    const int64_t rows_per_block = (M + gridDim.y - 1) / gridDim.y;
-    const int64_t r0 = blockIdx.y * rows_per_block;
-    int64_t r1 = r0 + rows_per_block; if (r1 > M) r1 = M;
-    uint4 xs[MAXI], gs[MAXI];
-    float s0[8], s1[8], mu[8], is[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { s0[e] = 0.f; s1[e] = 0.f; mu[e] = mean[c0 + e]; is[e] = invstd[c0 + e]; }
-#pragma unroll
-    for (int i = 0; i < MAXI; ++i) {
-        const int64_t r = r0 + ty + (int64_t)lanes * i;
-        xs[i] = make_uint4(0, 0, 0, 0); gs[i] = make_uint4(0, 0, 0, 0);
-        if (r < r1) {
-            xs[i] = *(const uint4 *)(x + r * C + c0);
-            gs[i] = *(const uint4 *)(dy + r * C + c0);
-            if (relu) {
-                const uint4 yv = *(const uint4 *)(y + r * C + c0);
-                const bf16 *yy = (const bf16 *)&yv; bf16 *gg = (bf16 *)&gs[i];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) if (!(__bfloat162float(yy[e]) > 0.f)) gg[e] = __float2bfloat16_rn(0.f);
-            }
-            const bf16 *xx = (const bf16 *)&xs[i], *gg = (const bf16 *)&gs[i];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float g = __bfloat162float(gg[e]);
-                s0[e] += g; s1[e] += g * ((__bfloat162float(xx[e]) - mu[e]) * is[e]);
-            }
-        }
-    }
-    __shared__ float sh[256 * 17];
-    __shared__ float coef[3][256];                    // per channel of this block: a, b, k
-    float *mine = sh + threadIdx.x * 17;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { mine[e] = s0[e]; mine[8 + e] = s1[e]; }
-    __syncthreads();
-    for (int stride = lanes >> 1; stride > 0; stride >>= 1) {
-        if (ty < stride) {
-            const float *other = sh + (threadIdx.x + stride * opb) * 17;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) mine[e] += other[e];
-        }
-        __syncthreads();
-    }
-    if (ty == 0) {
-        float *dst = bsum + (size_t)(blockIdx.y % kBnSumCopies) * 2 * C;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { atomicAdd(dst + c0 + e, mine[e]); atomicAdd(dst + C + c0 + e, mine[8 + e]); }
-    }
-    // ---- grid-wide barrier
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        atomicAdd(counter, 1u);
-        const unsigned int total = gridDim.x * gridDim.y;
-        const long long t0 = clock64();
-        unsigned int v;
-        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); }
-        while (v < total && (clock64() - t0 < 6000000000LL || ((*err = 1), false)));
-    }
-    __syncthreads();
-    if (ty == 0) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int c = c0 + e;
-            float sg = 0.f, sgx = 0.f;
-#pragma unroll
-            for (int k = 0; k < kBnSumCopies; ++k) { sg += __ldcg(bsum + (2 * k) * C + c); sgx += __ldcg(bsum + (2 * k + 1) * C + c); }
-            const float a = gamma[c] * is[e], c1 = sg / (float)M, c2 = sgx / (float)M;
-            coef[0][tx * 8 + e] = a; coef[1][tx * 8 + e] = -a * c2 * is[e]; coef[2][tx * 8 + e] = -a * c1 + a * c2 * is[e] * mu[e];
-            if (blockIdx.y == 0) { dbeta[c] = sg; dgamma[c] = sgx; }
-        }
-    }
-    __syncthreads();
-    float ca[8], cb[8], ck[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { ca[e] = coef[0][tx * 8 + e]; cb[e] = coef[1][tx * 8 + e]; ck[e] = coef[2][tx * 8 + e]; }
-#pragma unroll
-    for (int i = 0; i < MAXI; ++i) {
-        const int64_t r = r0 + ty + (int64_t)lanes * i;
-        if (r < r1) {
-            const bf16 *xx = (const bf16 *)&xs[i], *gg = (const bf16 *)&gs[i];
-            __align__(16) bf16 ov[8], rv[8];
-            uint4 pold = make_uint4(0, 0, 0, 0), rold = make_uint4(0, 0, 0, 0);
-            if (acc_dx) pold = *(const uint4 *)(dx + r * C + c0);
-            if (dres && acc_dres) rold = *(const uint4 *)(dres + r * C + c0);
-            const bf16 *po = (const bf16 *)&pold, *ro = (const bf16 *)&rold;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float g = __bfloat162float(gg[e]);
-                float d = fmaf(ca[e], g, fmaf(cb[e], __bfloat162float(xx[e]), ck[e]));
-                if (acc_dx) d += __bfloat162float(po[e]);
-                ov[e] = __float2bfloat16_rn(d);
-                if (dres) { float rr = g; if (acc_dres) rr += __bfloat162float(ro[e]); rv[e] = __float2bfloat16_rn(rr); }
-            }
-            *(uint4 *)(dx + r * C + c0) = *(uint4 *)ov;
-            if (dres) *(uint4 *)(dres + r * C + c0) = *(uint4 *)rv;
-        }
-    }
-}
-
 int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx, void *dres, int dt, int64_t M, int C,
                          float *bsum, const float *gamma, float *dgamma, float *dbeta, bool relu, bool acc_dx,
-                         bool acc_dres, bool sums_ready, const BnWork &w, cudaStream_t s, unsigned int *coop_counter,
-                         int *coop_err) {
+                         bool acc_dres, bool sums_ready, const BnWork &w, cudaStream_t s) {
     B2_CHECK(dt == DT_BF16 && C % 8 == 0, B2_ERR_ARG, "bn fused: bf16 activations with C %% 8 == 0 only");
-    bool coef_ready = false;
-    // measured (r01): letting the last reduce block derive the coefficients once is slower (1.019 vs 1.001 ms/step)
-    // than every apply block re-deriving them -- the serial tail costs more than the redundant loads.  Opt-in.
-    static const bool last_block_coef = [] { const char *e = getenv("B2_BN_COEF_LAST"); return e && e[0] == '1'; }();
-    // measured (r01): parity-green but 12% slower end to end (1.136 vs 1.011 ms/step): the kernel needs
-    // the whole register file of an SM (233-255 regs x 256 threads) and therefore cannot share an SM with
-    // the weight-gradient kernels that run concurrently on their own stream.  B2_BN_BWD_COOP=1 enables it.
-    static const bool allow_coop = [] { const char *e = getenv("B2_BN_BWD_COOP"); return e && e[0] == '1'; }();
-    if (allow_coop && coop_counter && !sums_ready) {
-        const int opb = C / 8 < 32 ? C / 8 : 32;
-        if ((C / 8) % opb == 0 && 256 % opb == 0) {
-            const int gx = (C / 8) / opb, lanes = 256 / opb;
-            int gy = kNumSMs / gx; if (gy < 1) gy = 1;
-            const int64_t rows_per_block = (M + gy - 1) / gy;
-            const int64_t items = (rows_per_block + lanes - 1) / lanes;
-            if (items <= 14 && gx * gy <= kNumSMs) {
-                dim3 grid(gx, gy);
-                if (items <= 8) {
-                    B2_LAUNCH((k_bn_bwd_coop<8>), grid, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, (bf16 *)dx,
-                              (bf16 *)dres, w.mean, w.invstd, gamma, dgamma, dbeta, bsum, coop_counter, coop_err, M, C, opb, relu,
-                              acc_dx, acc_dres);
-                } else {
-                    B2_LAUNCH((k_bn_bwd_coop<14>), grid, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, (bf16 *)dx,
-                              (bf16 *)dres, w.mean, w.invstd, gamma, dgamma, dbeta, bsum, coop_counter, coop_err, M, C, opb, relu,
-                              acc_dx, acc_dres);
-                }
-                return 0;
-            }
-        }
-    }
-    if (!sums_ready && M <= 1024 && C >= 512) {      // measured: wins only for the 1x1-spatial stage
+    if (!sums_ready && M <= 1024 && C >= 512) {      // measured (r01): wins only for the 1x1-spatial stage
         B2_LAUNCH((k_bn_bwd_small<bf16>), C / 8, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, (bf16 *)dx,
                   (bf16 *)dres, w.mean, w.invstd, gamma, dgamma, dbeta, M, C, relu, acc_dx, acc_dres);
         return 0;
     }
     if (!sums_ready) {
-    int opb = C / 8 < 32 ? C / 8 : 32;
-    B2_CHECK((C / 8) % opb == 0 && 256 % opb == 0, B2_ERR_ARG, "bn fused: unsupported channel count %d", C);
-    int gx = (C / 8) / opb;
-    int lanes = 256 / opb;
-    int64_t want = (kNumSMs * 2 + gx - 1) / gx;
-    int64_t maxb = ceil_div(M, (int64_t)lanes * 4); if (want > maxb) want = maxb; if (want < 1) want = 1;
-    dim3 grid(gx, (unsigned)want);
-    B2_LAUNCH((k_bn_bwd_reduce_atomic<bf16>), grid, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, w.mean, w.invstd,
-              relu, M, C, opb, bsum, (coop_counter && last_block_coef) ? coop_counter + 1 : nullptr, gamma, dgamma, dbeta, w.coef);
-    coef_ready = coop_counter != nullptr && last_block_coef;
+        // (only BatchNorms whose output gradient is not finalised by a tcgen05 dgrad: the stem's, the last block's)
+        int opb = C / 8 < 32 ? C / 8 : 32;
+        B2_CHECK((C / 8) % opb == 0 && 256 % opb == 0, B2_ERR_ARG, "bn fused: unsupported channel count %d", C);
+        int gx = (C / 8) / opb;
+        int lanes = 256 / opb;
+        int64_t want = (kNumSMs * 2 + gx - 1) / gx;
+        int64_t maxb = ceil_div(M, (int64_t)lanes * 4); if (want > maxb) want = maxb; if (want < 1) want = 1;
+        dim3 grid(gx, (unsigned)want);
+        B2_LAUNCH((k_bn_bwd_reduce_atomic<bf16>), grid, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, w.mean, w.invstd,
+                  relu, M, C, opb, bsum);
     }
     int64_t total = M * C;
     int64_t blocks = ceil_div(total / 8, 256); if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
     B2_LAUNCH((k_bn_bwd_apply_fused<bf16, 8>), (int)blocks, 256, 3 * C * sizeof(float), s, (const bf16 *)x, (const bf16 *)y,
               (const bf16 *)dy, (bf16 *)dx, (bf16 *)dres, w.mean, w.invstd, bsum, gamma, dgamma, dbeta, M, relu, acc_dx, acc_dres,
-              total, C, coef_ready ? (const float *)w.coef : (const float *)nullptr);
+              total, C);
     return 0;
 }
 

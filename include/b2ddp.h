@@ -128,6 +128,13 @@ int b2_model_read_activation(b2_model *m, int op, int want_grad, float *out, int
 int b2_conv_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, int pad, int mode,
                  int use_umma, int acc, const void *x_bf16, const float *w_master,
                  const void *dy_bf16, void *out, void *stream);
+/* one fprop launch with the fused BatchNorm(+residual, ReLU) epilogue, exactly as the model issues it for
+ * every conv+BN pair (torchvision resnet.py:92-94: conv -> bn -> relu): z = conv(x), y = relu?(bn_train(z) + res).
+ * info3 (optional) returns {output-channel tile, persistent grid, tile count}. */
+int b2_conv_bn_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, int pad, int relu,
+                    const void *x_bf16, const float *w_master, const void *res_bf16, const float *gamma,
+                    const float *beta, void *z_out, void *y_out, float *mean_out, float *invstd_out,
+                    int *info3, void *stream);
 
 /* ---- next rows: input transform and eval counters -----------------------------
  * transforms.ToTensor() + Normalize(mean, std) (cifar_example_ddp.py:61-63) on the device:
