@@ -49,7 +49,7 @@ _SIGS = {
     "b2_preprocess_u8": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp]),
     "b2_argmax_count": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "b2_conv_test": (_i, [_i] * 11 + [_vp, _vp, _vp, _vp, _vp]),
-    "b2_conv_bn_test": (_i, [_i] * 9 + [_vp] * 11),
+    "b2_conv_bn_test": (_i, [_i] * 9 + [_vp] * 12),
     "b2_ce_loss_grad": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "b2_ce_loss_grad_running": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "b2_sgd": (_i, [_vp, _vp, _vp, _i64, _f, _f, _f, _i, _vp, _vp]),
@@ -65,6 +65,18 @@ _SIGS = {
     "b2_comm_register": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i64]),
     "b2_comm_barrier": (_i, [_vp]),
     "b2_comm_flag_bytes": (_i, []),
+    "b2_vmm_query": (_i, [_i, C.POINTER(_i), C.POINTER(_i64)]),
+    "b2_vmm_alloc": (_i, [_i, _i64, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i)]),
+    "b2_vmm_import": (_i, [_i, _i, _i64, C.POINTER(_vp)]),
+    "b2_mc_create": (_i, [_i, _i64, C.POINTER(_i64), C.POINTER(_i)]),
+    "b2_mc_import": (_i, [_i, C.POINTER(_i64)]),
+    "b2_mc_add_device": (_i, [_i64, _i]),
+    "b2_mc_bind_and_map": (_i, [_i64, _i64, _i64, _i, C.POINTER(_vp)]),
+    "b2_vmm_close_fd": (_i, [_i]),
+    "b2_vmm_release_all": (_i, []),
+    "b2_comm_register_multicast": (_i, [_vp, _vp]),
+    "b2_comm_set_nvls": (_i, [_i]),
+    "b2_comm_nvls_active": (_i, []),
     "b2_comm_check": (_i, []),
     "b2_allreduce": (_i, [_i64, _f, _i, _vp]),
     "b2_allreduce_range": (_i, [_i64, _i64, _f, _i, _vp]),

@@ -272,8 +272,20 @@ int b2_conv_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, int p
     if (rc == 0) {
         if (use_umma) {
             if (!umma_conv_eligible(g)) { set_error("conv_test: shape not eligible for the tcgen05 path"); rc = B2_ERR_UNSUPPORTED; }
-            else if (mode == 0) { UmmaConvPlan pl; rc = umma_plan_fprop(g, (const bf16 *)x_bf16, w, (bf16 *)out, &pl); if (!rc) rc = umma_conv_launch(pl, s); }
-            else if (mode == 1) { UmmaConvPlan pl; rc = umma_plan_dgrad(g, (const bf16 *)dy_bf16, w, (bf16 *)out, acc != 0, &pl); if (!rc) rc = umma_conv_launch(pl, s); }
+            else if (mode == 0 || mode == 1) {
+                UmmaConvPlan pl;
+                rc = mode == 0 ? umma_plan_fprop(g, (const bf16 *)x_bf16, w, (bf16 *)out, &pl)
+                               : umma_plan_dgrad(g, (const bf16 *)dy_bf16, w, (bf16 *)out, acc != 0, &pl);
+                float *skw = nullptr;
+                if (!rc && pl.p.splits > 1) {
+                    const size_t nf = umma_conv_workspace_floats(pl) + umma_conv_ticket_words(pl);
+                    if (cudaMalloc(&skw, nf * 4) != cudaSuccess || cudaMemsetAsync(skw, 0, nf * 4, s) != cudaSuccess) rc = B2_ERR_CUDA;
+                    else umma_conv_set_workspace(&pl, skw, (unsigned int *)(skw + umma_conv_workspace_floats(pl)));
+                }
+                if (!rc) rc = umma_conv_launch(pl, s);
+                cudaStreamSynchronize(s);
+                cudaFree(skw);
+            }
             else {
                 UmmaWgradPlan pl; rc = umma_plan_wgrad(g, (const bf16 *)x_bf16, (const bf16 *)dy_bf16, (float *)out, ws, wsf, acc != 0 /* deterministic */, &pl);
                 if (!rc && (pl.p.atomic || pl.need_zero)) { cudaError_t ze = cudaMemsetAsync(out, 0, (size_t)Co * taps * Ci * 4, s); if (ze != cudaSuccess) rc = B2_ERR_CUDA; }
@@ -299,7 +311,7 @@ int b2_conv_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, int p
 // mean / invstd (fp32 [Co]) of the training-mode batch statistics.
 int b2_conv_bn_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, int pad, int relu, const void *x_bf16,
                     const float *w_master, const void *res_bf16, const float *gamma, const float *beta, void *z_out, void *y_out,
-                    float *mean_out, float *invstd_out, int *info3, void *stream) {
+                    float *mean_out, float *invstd_out, int *info3, long long *timeline13, void *stream) {
     GUARD_BEGIN
     cudaStream_t s = (cudaStream_t)stream;
     ConvGeom g{};
@@ -309,24 +321,32 @@ int b2_conv_bn_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, in
     bf16 *w = nullptr; float *scratch = nullptr;
     const size_t wn = (size_t)Co * k * k * Ci, sums = 2 * (size_t)kBnSumCopies * Co;
     B2_CUDA(cudaMalloc(&w, wn * 2));
-    B2_CUDA(cudaMalloc(&scratch, (sums + 8) * 4));
-    B2_CUDA(cudaMemsetAsync(scratch, 0, (sums + 8) * 4, s));
+    B2_CUDA(cudaMalloc(&scratch, (sums + 8 + 32) * 4));
+    B2_CUDA(cudaMemsetAsync(scratch, 0, (sums + 8 + 32) * 4, s));
     int rc = op_f32_to_bf16(w_master, w, (int64_t)wn, s);
     UmmaConvPlan pl;
     if (!rc) rc = umma_plan_fprop(g, (const bf16 *)x_bf16, w, (bf16 *)z_out, &pl);
     if (!rc) rc = umma_conv_check_coresident(pl);
+    float *skw = nullptr;
+    if (!rc && pl.p.splits > 1) {
+        const size_t nf = umma_conv_workspace_floats(pl) + umma_conv_ticket_words(pl);
+        if (cudaMalloc(&skw, nf * 4) != cudaSuccess || cudaMemsetAsync(skw, 0, nf * 4, s) != cudaSuccess) rc = B2_ERR_CUDA;
+        else umma_conv_set_workspace(&pl, skw, (unsigned int *)(skw + umma_conv_workspace_floats(pl)));
+    }
     if (!rc) {
         ConvParams &q = pl.p;
         q.stats = scratch;
         q.fuse_bn = 1; q.fb_y = (bf16 *)y_out; q.fb_res = (const bf16 *)res_bf16; q.fb_gamma = gamma; q.fb_beta = beta;
         q.fb_save_mean = mean_out; q.fb_save_invstd = invstd_out; q.fb_running_mean = nullptr; q.fb_running_var = nullptr;
         q.fb_sync = (unsigned int *)(scratch + sums); q.fb_err = (int *)(scratch + sums + 4);
-        q.fb_count = (float)g.M(); q.fb_eps = 1e-5f; q.fb_momentum = 0.1f; q.fb_relu = relu ? 1 : 0;
-        if (info3) { info3[0] = pl.bn_tile; info3[1] = pl.grid; info3[2] = pl.p.total_tiles; }
+        q.fb_count = (float)g.M(); q.fb_inv_count = 1.0 / (double)g.M(); q.fb_eps = 1e-5f; q.fb_momentum = 0.1f; q.fb_relu = relu ? 1 : 0;
+        if (timeline13) q.timeline = (long long *)(scratch + sums + 8);
+        if (info3) { info3[0] = pl.bn_tile; info3[1] = pl.grid; info3[2] = pl.p.total_tiles * 100 + pl.p.splits; }
         rc = umma_conv_launch(pl, s);
     }
     cudaError_t e = cudaStreamSynchronize(s);
-    cudaFree(w); cudaFree(scratch);
+    if (timeline13 && e == cudaSuccess) e = cudaMemcpy(timeline13, scratch + sums + 8, 13 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(w); cudaFree(scratch); cudaFree(skw);
     if (rc == 0 && e != cudaSuccess) { set_error("conv_bn_test: %s", cudaGetErrorString(e)); rc = B2_ERR_CUDA; }
     return rc;
     GUARD_END

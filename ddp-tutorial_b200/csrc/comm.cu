@@ -39,6 +39,8 @@ struct CommState {
     bool registered = false;
     CommPtrs ptrs{};
     int64_t n_elems = 0;
+    float *mc_grads = nullptr, *mc_params = nullptr;   // NVSwitch multicast addresses of the same buffers (NVLS), or null
+    bool use_nvls = false;
     uint32_t *epoch = nullptr;     // local device memory: per-block barrier epoch [2][kCommBlocks]
     int *err = nullptr;            // local device word: set by a kernel whose flag wait timed out
     std::vector<void *> allocs;
@@ -187,6 +189,77 @@ k_allreduce(const CommPtrs P, int rank, float *__restrict__ mom_buf, int64_t off
     }
 }
 
+
+// ---- NVLS: in-switch reduction / broadcast through the multicast mapping (comm_vmm.cu) ---------------
+__device__ __forceinline__ float4 mc_ld_reduce_f4(const float *mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st_f4(float *mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Same contract as k_allreduce, but the W-way sum is ONE multimem.ld_reduce per float4 (the NVSwitch reads the W
+// replicas and adds them in fp32) and the result / updated parameters go out with ONE multimem.st (the switch
+// writes all W replicas): each GPU moves 1/W of the bytes over its own links instead of (W-1)/W.
+template <int W, int MODE, bool ONESHOT>
+__global__ void __launch_bounds__(kCommThreads)
+k_allreduce_nvls(const CommPtrs P, int rank, float *__restrict__ mc_grads, float *__restrict__ mc_params, float *__restrict__ mom_buf,
+                 int64_t off, int64_t n4, float scale, float lr, float momentum, int first, bf16 *__restrict__ mirror,
+                 uint32_t *epoch_mem, int *err) {
+    pdl_sync();
+    peer_barrier<W, false>(P, rank, epoch_mem, 0, err);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ONESHOT) {
+        // small buckets: every rank asks the switch for the whole sum and updates its own replica
+        if (MODE == 1) {
+            for (int64_t i = tid; i < n4; i += stride) {
+                const int64_t e = off + i * 4;
+                float4 acc = f4_scale(mc_ld_reduce_f4(mc_grads + e), scale);
+                float4 p = *(float4 *)(P.params[rank] + e), m = first ? acc : *(float4 *)(mom_buf + e);
+                sgd_apply(p, m, acc, lr, momentum, first);
+                *(float4 *)(mom_buf + e) = m;
+                *(float4 *)(P.params[rank] + e) = p;
+                if (mirror) st_bf16x4(mirror + e, p);
+            }
+            peer_barrier<W, false>(P, rank, epoch_mem, 1, err);      // peers are done reading my grads
+        } else {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int64_t e = off + tid * 4;
+            if (tid < n4) acc = f4_scale(mc_ld_reduce_f4(mc_grads + e), scale);
+            peer_barrier<W, false>(P, rank, epoch_mem, 1, err);
+            if (tid < n4) *(float4 *)(P.grads[rank] + e) = acc;
+        }
+    } else {
+        const int64_t per = (n4 + W - 1) / W;
+        const int64_t lo = (int64_t)rank * per;
+        int64_t hi = lo + per; if (hi > n4) hi = n4;
+#pragma unroll 4
+        for (int64_t i = lo + tid; i < hi; i += stride) {
+            const int64_t e = off + i * 4;
+            float4 acc = f4_scale(mc_ld_reduce_f4(mc_grads + e), scale);
+            if (MODE == 1) {
+                float4 p = *(float4 *)(P.params[rank] + e), m = first ? acc : *(float4 *)(mom_buf + e);
+                sgd_apply(p, m, acc, lr, momentum, first);
+                *(float4 *)(mom_buf + e) = m;
+                mc_st_f4(mc_params + e, p);                     // all W replicas, mine included
+            } else {
+                mc_st_f4(mc_grads + e, acc);
+            }
+        }
+        peer_barrier<W>(P, rank, epoch_mem, 1, err);          // all slices have landed everywhere
+        if (MODE == 1 && mirror) {
+            for (int64_t i = tid; i < n4; i += stride) {
+                const int64_t e = off + i * 4;
+                st_bf16x4(mirror + e, ld_peer_f4(P.params[rank] + e));
+            }
+        }
+    }
+}
+
 template <int W>
 __global__ void __launch_bounds__(kCommThreads)
 k_barrier_only(const CommPtrs P, int rank, uint32_t *epoch_mem, int *err) {
@@ -216,8 +289,13 @@ static int launch_allreduce(int64_t off, int64_t n, float *m, float scale, float
     // small messages: only as many blocks as there is data (same on every rank: a function of n)
     int blocks = kCommBlocks;
     if (oneshot) { int64_t need = (n4 + kCommThreads - 1) / kCommThreads; if (need < blocks) blocks = need < 1 ? 1 : (int)need; }
+    const bool nvls = c.use_nvls && c.mc_grads && (MODE == 0 || c.mc_params) && c.world > 1;
 #define LAUNCH_W(Wv)                                                                                              \
-    if (oneshot) { B2_LAUNCH((k_allreduce<Wv, MODE, true>), blocks, kCommThreads, 0, s, c.ptrs, c.rank, m, off, n4, \
+    if (nvls && oneshot) { B2_LAUNCH((k_allreduce_nvls<Wv, MODE, true>), blocks, kCommThreads, 0, s, c.ptrs, c.rank, c.mc_grads, c.mc_params, m, \
+                                     off, n4, scale, lr, momentum, first, mirror, c.epoch, c.err); }                  \
+    else if (nvls) { B2_LAUNCH((k_allreduce_nvls<Wv, MODE, false>), kCommBlocks, kCommThreads, 0, s, c.ptrs, c.rank, c.mc_grads, c.mc_params, m, \
+                               off, n4, scale, lr, momentum, first, mirror, c.epoch, c.err); }                        \
+    else if (oneshot) { B2_LAUNCH((k_allreduce<Wv, MODE, true>), blocks, kCommThreads, 0, s, c.ptrs, c.rank, m, off, n4, \
                              scale, lr, momentum, first, mirror, c.epoch, c.err); }                                   \
     else { B2_LAUNCH((k_allreduce<Wv, MODE, false>), kCommBlocks, kCommThreads, 0, s, c.ptrs, c.rank, m, off, n4, scale,   \
                      lr, momentum, first, mirror, c.epoch, c.err); }
@@ -322,8 +400,21 @@ int b2_comm_register(void *const *grads, void *const *params, void *const *flags
     }
     c.n_elems = n_elems;
     c.registered = true;
+    c.mc_grads = c.mc_params = nullptr; c.use_nvls = false;      // a new registration starts without multicast
     return 0;
 }
+
+/* NVLS: multicast addresses of the SAME gradient / parameter buffers registered above (comm_vmm.cu); NULL disables */
+int b2_comm_register_multicast(void *mc_grads, void *mc_params) {
+    CommState &c = g_comm;
+    B2_CHECK(c.inited && c.registered, B2_ERR_STATE, "comm: register the peer buffers first");
+    c.mc_grads = (float *)mc_grads; c.mc_params = (float *)mc_params;
+    c.use_nvls = mc_grads != nullptr;
+    return 0;
+}
+/* 1: all-reduce through the switch (multimem) when multicast addresses are registered; 0: peer loads/stores */
+int b2_comm_set_nvls(int enable) { g_comm.use_nvls = enable != 0 && g_comm.mc_grads != nullptr; return 0; }
+int b2_comm_nvls_active(void) { return g_comm.use_nvls ? 1 : 0; }
 
 int b2_comm_flag_bytes(void) { return 2 * kMaxWorld * kFlagStride * (int)sizeof(uint32_t); }
 

@@ -107,6 +107,12 @@ bool umma_conv_eligible(const ConvGeom &g) {
     return true;
 }
 
+bool umma_stem_supported(const ConvGeom &g, const ConvGeom &v, int kpad) {
+    // the gather code is written for exactly this geometry (torchvision's stem on CIFAR-sized input)
+    return g.Ci == 3 && g.Hi == 32 && g.Wi == 32 && g.kh == 7 && g.kw == 7 && g.stride == 2 && g.pad == 3 && g.Ho == 16 && g.Wo == 16 &&
+           g.Co == 64 && kpad == 192 && v.Ci == 192 && v.kh == 1 && v.Ho == 16 && v.Wo == 16;
+}
+
 // does a tap at source offset d (source = box*step + d) ever touch [0, src) for box in [0, nbox)?
 static bool tap_alive(int d, int step, int nbox, int src) {
     for (int b = 0; b < nbox; ++b) { int v = b * step + d; if (v >= 0 && v < src) return true; }
@@ -116,6 +122,7 @@ static bool tap_alive(int d, int step, int nbox, int src) {
 // =================================================================================
 // device: fprop / dgrad
 // =================================================================================
+constexpr int kStemXsElemsC = 3 * 21 * 40;
 template <int BN_TILE>
 struct ConvCfg {
     static constexpr int kStages = BN_TILE == 128 ? 5 : 6;
@@ -123,28 +130,94 @@ struct ConvCfg {
     static constexpr int kBBytes = BN_TILE * 128;          // BN_TILE channel rows x 64 bf16 (or 64 k-rows x BN_TILE)
     static constexpr int kStagingBytes = (BN_TILE / 64) * 16384;   // [half][128 rows][128 B], 128B-swizzled
     static constexpr int kRedFloats = 4 * 2 * BN_TILE;     // per epilogue warp: [2][BN_TILE] partial sums
-    static constexpr int kSmem = kStages * (kABytes + kBBytes) + kStagingBytes + (kRedFloats + 2 * BN_TILE) * 4 + 256 /*barriers*/ + 1024 /*align*/;
+    static constexpr int kSmem = kStages * (kABytes + kBBytes) + kStagingBytes + (kRedFloats + 2 * BN_TILE) * 4 + 256 /*barriers*/ +
+                                 2 * kStemXsElemsC * 2 /*stem input windows*/ + 1024 /*align*/;
     static constexpr int kTmemCols = 2 * BN_TILE;          // two accumulator buffers
     static constexpr int kCPR = BN_TILE / 8;               // 16-byte chunks per output row
 };
 constexpr int kConvThreads = 224;     // warps: 0 A-TMA, 1 B-TMA, 2 MMA, 3..6 epilogue
+constexpr int kStemExtraThreads = 128; // stem variants: 4 more warps gather im2col rows into the A stages
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-struct TileCoord { int z, n, n_blk, h_blk, ch0, m; };
+// ---- stem gather (shared by k_conv<64, true> and k_wgrad<true>) ----------------------------------------------------
+// Geometry is fixed: 3 x 32 x 32 fp32 image, 7x7 / stride 2 / pad 3, 16x16 outputs, tile = 8 output rows x 16 columns
+// of one image.  The 21 input rows a tile needs are staged as bf16 [3][21][40] (3 zero columns left, 5 right), so the
+// 8 consecutive input pixels of im2col chunk (c, kh) at output column ow start at element 2*ow of row 2*oh_l + kh.
+constexpr int kStemXsRow = 40, kStemXsRows = 21, kStemXsElems = 3 * kStemXsRows * kStemXsRow;
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void stem_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+struct StemRaw { float4 v[4]; };
+// issue the global loads of the 3 x 21 input rows of (image n, row half h_blk); 504 float4, up to 4 per thread
+__device__ __forceinline__ void stem_load(const float *__restrict__ x, int n, int h_blk, int gt, StemRaw &raw) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int idx = gt + u * 128;
+        raw.v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < 3 * kStemXsRows * 8) {
+            const int c = idx / (kStemXsRows * 8), rem = idx - c * (kStemXsRows * 8), rr = rem >> 3, q4 = rem & 7;
+            const int ih = h_blk * 16 - 3 + rr;
+            if (ih >= 0 && ih < 32) raw.v[u] = __ldg((const float4 *)(x + (((int64_t)n * 3 + c) * 32 + ih) * 32) + q4);
+        }
+    }
+}
+__device__ __forceinline__ void stem_store(bf16 *xs, int gt, const StemRaw &raw) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int idx = gt + u * 128;
+        if (idx < 3 * kStemXsRows * 8) {
+            const int c = idx / (kStemXsRows * 8), rem = idx - c * (kStemXsRows * 8), rr = rem >> 3, q4 = rem & 7;
+            bf16 *d = xs + (c * kStemXsRows + rr) * kStemXsRow + 3 + q4 * 4;
+            d[0] = __float2bfloat16_rn(raw.v[u].x); d[1] = __float2bfloat16_rn(raw.v[u].y);
+            d[2] = __float2bfloat16_rn(raw.v[u].z); d[3] = __float2bfloat16_rn(raw.v[u].w);
+        }
+    }
+}
+// im2col k-chunk kc (64 columns = 8 (c, kh) groups of 8 pixels) of tile row r = oh_l * 16 + ow -> 128B-swizzled stage row
+__device__ __forceinline__ void stem_build_chunk(const bf16 *xs, int r, int kc, uint8_t *stage) {
+    const int oh_l = r >> 4, ow = r & 15;
+    uint8_t *row = stage + r * 128;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+        const int j = kc * 8 + jj;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (j < 21) {
+            const int c = j / 7, kh = j - c * 7;
+            const uint32_t *src = (const uint32_t *)(xs + (c * kStemXsRows + 2 * oh_l + kh) * kStemXsRow + 2 * ow);
+            v = make_uint4(src[0], src[1], src[2], src[3]);
+        }
+        *(uint4 *)(row + ((jj ^ (r & 7)) << 4)) = v;
+    }
+}
+
+struct TileCoord { int z, n, n_blk, h_blk, ch0, m, t, split, ks0, ks1; };
+// work item w = tile * splits + split; tile = (class * n_tiles + n) * m_tiles + m; a split owns the k-steps [ks0, ks1)
 template <int BN_TILE>
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams &p, int t) {
+__device__ __forceinline__ TileCoord decode_work(const ConvParams &p, int w) {
     TileCoord c;
-    c.m = t % p.m_tiles;
-    const int r = t / p.m_tiles;
+    c.t = w / p.splits; c.split = w - c.t * p.splits;
+    c.m = c.t % p.m_tiles;
+    const int r = c.t / p.m_tiles;
     c.n = r % p.n_tiles; c.z = r / p.n_tiles;
     c.n_blk = c.m / p.h_blocks; c.h_blk = c.m - c.n_blk * p.h_blocks;
     c.ch0 = c.n * BN_TILE;
+    const int ks_all = p.cls[c.z].ntaps * p.c_chunks;
+    c.ks0 = c.split * ks_all / p.splits; c.ks1 = (c.split + 1) * ks_all / p.splits;
     return c;
 }
+// global element offset of tile row `row`, 8-channel chunk `chunk`
+__device__ __forceinline__ int64_t row_offset(const ConvParams &p, const TileCoord &tc, int row, int chunk, int oh, int ow) {
+    const int w_l = row & (p.BW - 1);
+    const int tt = row >> p.lgBW;
+    const int h_l = tt & (p.BH - 1), n_l = tt >> p.lgBH;
+    const int n = tc.n_blk * p.BN + n_l;
+    const int h = (tc.h_blk * p.BH + h_l) * p.os + oh;
+    const int w = w_l * p.os + ow;
+    return (((int64_t)n * p.out_H + h) * p.out_W + w) * p.out_C + tc.ch0 + chunk * 8;
+}
 
-template <int BN_TILE>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int BN_TILE, bool STEM>
+__global__ void __launch_bounds__(kConvThreads + (STEM ? kStemExtraThreads : 0), 1)
 k_conv(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
        const __grid_constant__ ConvParams p) {
     using Cfg = ConvCfg<BN_TILE>;
@@ -159,9 +232,15 @@ k_conv(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtens
     uint64_t *bars = (uint64_t *)(sSS + 2 * BN_TILE);
     uint64_t *full = bars, *empty = bars + S, *tfull = bars + 2 * S, *tempty = bars + 2 * S + 2;
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * S + 4);
+    uint32_t *s_ticket = tmem_slot + 1;
+    bf16 *sXs = (bf16 *)(bars + 2 * S + 6);                          // STEM: two staged input windows
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_work = p.total_tiles * p.splits;
+    long long *tl = (p.timeline && blockIdx.x == 0) ? p.timeline : nullptr;
+#define TL(i) do { if (tl) tl[i] = clock64(); } while (0)
     if (threadIdx.x == 0) {
+        TL(0);
         prefetch_tmap(&a_map); prefetch_tmap(&b_map);
         for (int i = 0; i < S; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
@@ -173,18 +252,51 @@ k_conv(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtens
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TL(1);
     pdl_wait();                    // everything below touches global memory of earlier kernels
+    if (threadIdx.x == 0) TL(2);
 
-    if (warp == 0) {
+    if (STEM && warp >= 7) {
+        // ---------------- stem: gather im2col rows from the fp32 image into the A stages (no TMA, no HBM im2col buffer)
+        const int gt = threadIdx.x - kConvThreads;
+        for (int i = gt; i < 2 * kStemXsElems; i += kStemExtraThreads) sXs[i] = __float2bfloat16_rn(0.f);   // pad columns stay zero
+        stem_bar();
+        StemRaw raw;
+        int stage = 0; uint32_t phase = 0, it = 0;
+        if ((int)blockIdx.x < total_work) {
+            const TileCoord t0 = decode_work<BN_TILE>(p, blockIdx.x);
+            stem_load(p.stem_x, t0.n_blk, t0.h_blk, gt, raw);
+            stem_store(sXs, gt, raw);
+        }
+        stem_bar();
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+            const bf16 *xs = sXs + (it & 1) * kStemXsElems;
+            const bool more = w + (int)gridDim.x < total_work;
+            if (more) {                                     // next tile's rows: loads in flight while this tile is built
+                const TileCoord tn = decode_work<BN_TILE>(p, w + gridDim.x);
+                stem_load(p.stem_x, tn.n_blk, tn.h_blk, gt, raw);
+            }
+#pragma unroll
+            for (int kc = 0; kc < 3; ++kc) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                stem_build_chunk(xs, gt, kc, sA + stage * kA);
+                fence_proxy_async_smem();                   // generic-proxy stores -> visible to the tensor core's async reads
+                stem_bar();
+                if (gt == 0) mbar_arrive(&full[stage]);
+                if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+            if (more) stem_store(sXs + ((it + 1) & 1) * kStemXsElems, gt, raw);
+            stem_bar();
+        }
+    } else if (warp == 0) {
         // ---------------- TMA producer: activation (A) tiles
-        if (lane == 0) {
+        if (!STEM && lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const TileCoord tc = decode_tile<BN_TILE>(p, t);
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const TileCoord tc = decode_work<BN_TILE>(p, w);
                 const TapClass &cls = p.cls[tc.z];
-                const int ksteps = cls.ntaps * p.c_chunks;
-                int tap = 0, cc = 0;
-                for (int ks = 0; ks < ksteps; ++ks) {
+                int tap = tc.ks0 / p.c_chunks, cc = tc.ks0 - tap * p.c_chunks;
+                for (int ks = tc.ks0; ks < tc.ks1; ++ks) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], kA);
                     tma_load_4d(sA + stage * kA, &a_map, &full[stage], cc * 64, cls.dw[tap],
@@ -198,12 +310,11 @@ k_conv(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtens
         // ---------------- TMA producer: weight (B) tiles
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const TileCoord tc = decode_tile<BN_TILE>(p, t);
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const TileCoord tc = decode_work<BN_TILE>(p, w);
                 const TapClass &cls = p.cls[tc.z];
-                const int ksteps = cls.ntaps * p.c_chunks;
-                int tap = 0, cc = 0;
-                for (int ks = 0; ks < ksteps; ++ks) {
+                int tap = tc.ks0 / p.c_chunks, cc = tc.ks0 - tap * p.c_chunks;
+                for (int ks = tc.ks0; ks < tc.ks1; ++ks) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], kB);
                     uint8_t *dst = sB + stage * kB;
@@ -227,25 +338,26 @@ k_conv(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtens
             const uint32_t blbo = p.b_mn ? 8192 : kB;      // MN-major: distance between 64-channel atoms
             int stage = 0; uint32_t phase = 0;
             int it = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-                const TileCoord tc = decode_tile<BN_TILE>(p, t);
-                const int ksteps = p.cls[tc.z].ntaps * p.c_chunks;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+                const TileCoord tc = decode_work<BN_TILE>(p, w);
                 const int buf = it & 1;
                 mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN_TILE;
-                for (int ks = 0; ks < ksteps; ++ks) {
+                for (int ks = tc.ks0; ks < tc.ks1; ++ks) {
                     mbar_wait(&full[stage], phase);
+                    if (it == 0 && ks == tc.ks0) TL(3);
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(sA + stage * kA), b0 = smem_u32(sB + stage * kB);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         mma_bf16_ss(d_tmem, make_desc_sw128(a0 + k * 32, 16, 1024), make_desc_sw128(b0 + k * bstep, blbo, 1024), idesc,
-                                    (ks > 0 || k > 0) ? 1u : 0u);
+                                    (ks > tc.ks0 || k > 0) ? 1u : 0u);
                     mma_commit(&empty[stage]);
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
                 mma_commit(&tfull[buf]);
+                if (it == 0) TL(4);
             }
         }
     } else {
@@ -256,15 +368,19 @@ k_conv(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtens
         const int chunk = et % CPR, rsub = et / CPR;     // phase B: fixed 8-channel chunk, rows rsub + i * (128 / CPR)
         const int half = chunk >> 3, c8 = chunk & 7;
         const bool want_fwd = p.stats != nullptr, want_bwd = p.bn_bsum != nullptr;
-        int it = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-            const TileCoord tc = decode_tile<BN_TILE>(p, t);
+        const bool split = p.splits > 1;
+        bf16 *__restrict__ outp = p.out;
+        int it = 0, last_tile = -1;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+            const TileCoord tc = decode_work<BN_TILE>(p, w);
             const TapClass &cls = p.cls[tc.z];
             const int buf = it & 1;
             mbar_wait(&tfull[buf], (it >> 1) & 1);
+            if (it == 0 && et == 0) TL(5);
             tc_fence_after();
-            // ---- phase A: TMEM -> bf16 -> swizzled staging rows
-            {
+            float *ws_tile = split ? p.ws + (int64_t)tc.t * 128 * BN_TILE : nullptr;
+            if (!split) {
+                // ---- phase A: TMEM -> bf16 -> swizzled staging rows
                 uint8_t *row_base = sStage + r * 128;
                 const int sw = r & 7;
 #pragma unroll
@@ -284,12 +400,40 @@ k_conv(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtens
                         *(uint4 *)(hb + ((cidx ^ sw) << 4)) = pk;
                     }
                 }
+            } else {
+                // ---- split-K: add this CTA's partial accumulators into the tile's fp32 workspace (L2 atomics)
+                float *wrow = ws_tile + r * BN_TILE;
+#pragma unroll
+                for (int j = 0; j < BN_TILE / 32; ++j) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + buf * BN_TILE + ((uint32_t)(q * 32) << 16) + j * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; ++k4)
+                        red_add_f4(wrow + j * 32 + k4 * 4, __uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]),
+                                   __uint_as_float(v[4 * k4 + 2]), __uint_as_float(v[4 * k4 + 3]));
+                }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[buf]);        // the MMA warp may start tile it+2 into this buffer
+            if (lane == 0) mbar_arrive(&tempty[buf]);        // the MMA warp may start item it+2 into this buffer
             epi_bar();
-            // ---- phase B: row-coalesced stores (+ read-modify-write, + BatchNorm sums)
+            if (split) {
+                // the CTA that adds the last partial finishes the tile (ticket per tile, self-resetting)
+                if (et == 0) {
+                    __threadfence();
+                    const uint32_t ticket = atomicAdd(p.tile_tickets + tc.t, 1u);
+                    if (ticket == (uint32_t)p.splits - 1) { p.tile_tickets[tc.t] = 0u; __threadfence(); }
+                    *s_ticket = ticket;
+                }
+                epi_bar();
+                const bool last = *s_ticket == (uint32_t)p.splits - 1;
+                epi_bar();                                   // everyone has read s_ticket before the next item overwrites it
+                if (!last) continue;
+            }
+            last_tile = tc.t;
+            if (it == 0 && et == 0) TL(6);
+            // ---- phase B: row-coalesced stores (+ read-modify-write, + BatchNorm sums), 4 rows in flight per thread
             float s0[8], s1[8], mu[8], is[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) { s0[e] = 0.f; s1[e] = 0.f; }
@@ -297,48 +441,58 @@ k_conv(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtens
 #pragma unroll
                 for (int e = 0; e < 8; ++e) { mu[e] = __ldg(p.bn_mean + tc.ch0 + chunk * 8 + e); is[e] = __ldg(p.bn_invstd + tc.ch0 + chunk * 8 + e); }
             }
-#pragma unroll 4
-            for (int i = 0; i < CPR; ++i) {
-                const int row = rsub + i * (128 / CPR);
-                const int w_l = row & (p.BW - 1);
-                const int tt = row >> p.lgBW;
-                const int h_l = tt & (p.BH - 1), n_l = tt >> p.lgBH;
-                const int n = tc.n_blk * p.BN + n_l;
-                const int h = (tc.h_blk * p.BH + h_l) * p.os + cls.oh;
-                const int w = w_l * p.os + cls.ow;
-                const int64_t off = (((int64_t)n * p.out_H + h) * p.out_W + w) * p.out_C + tc.ch0 + chunk * 8;
-                uint4 pk = *(const uint4 *)(sStage + half * 16384 + row * 128 + ((c8 ^ (row & 7)) << 4));
-                __nv_bfloat162 *p2 = (__nv_bfloat162 *)&pk;
-                if (p.acc) {
-                    const uint4 old = *(const uint4 *)(p.out + off);
-                    const __nv_bfloat162 *o2 = (const __nv_bfloat162 *)&old;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 a = __bfloat1622float2(p2[e]), b = __bfloat1622float2(o2[e]);
-                        p2[e] = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+            for (int i0 = 0; i0 < CPR; i0 += 4) {
+                int64_t off[4]; uint4 pk[4], old[4], yr[4], xr[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int row = rsub + (i0 + u) * (128 / CPR);
+                    off[u] = row_offset(p, tc, row, chunk, cls.oh, cls.ow);
+                    if (!split) pk[u] = *(const uint4 *)(sStage + half * 16384 + row * 128 + ((c8 ^ (row & 7)) << 4));
+                    else {
+                        float4 *wp = (float4 *)(ws_tile + row * BN_TILE + chunk * 8);
+                        const float4 a = __ldcg(wp), b = __ldcg(wp + 1);
+                        wp[0] = make_float4(0.f, 0.f, 0.f, 0.f); wp[1] = make_float4(0.f, 0.f, 0.f, 0.f);   // clean for the next launch
+                        __nv_bfloat162 *p2 = (__nv_bfloat162 *)&pk[u];
+                        p2[0] = __floats2bfloat162_rn(a.x, a.y); p2[1] = __floats2bfloat162_rn(a.z, a.w);
+                        p2[2] = __floats2bfloat162_rn(b.x, b.y); p2[3] = __floats2bfloat162_rn(b.z, b.w);
                     }
+                    if (p.acc) old[u] = *(const uint4 *)(outp + off[u]);
+                    if (want_bwd) { yr[u] = *(const uint4 *)(p.bn_y + off[u]); xr[u] = *(const uint4 *)(p.bn_x + off[u]); }
                 }
-                *(uint4 *)(p.out + off) = pk;
-                if (want_fwd) {                        // statistics of the values BatchNorm will read (bf16-rounded)
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 f = __bfloat1622float2(p2[e]);
-                        s0[2 * e] += f.x; s1[2 * e] = fmaf(f.x, f.x, s1[2 * e]);
-                        s0[2 * e + 1] += f.y; s1[2 * e + 1] = fmaf(f.y, f.y, s1[2 * e + 1]);
+                for (int u = 0; u < 4; ++u) {
+                    __nv_bfloat162 *p2 = (__nv_bfloat162 *)&pk[u];
+                    if (p.acc) {
+                        const __nv_bfloat162 *o2 = (const __nv_bfloat162 *)&old[u];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 a = __bfloat1622float2(p2[e]), b = __bfloat1622float2(o2[e]);
+                            p2[e] = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+                        }
                     }
-                } else if (want_bwd) {                 // g = dY*[y>0],  g*xhat  of the BatchNorm that produced this tensor
-                    const uint4 yr = *(const uint4 *)(p.bn_y + off), xr = *(const uint4 *)(p.bn_x + off);
-                    const __nv_bfloat162 *y2 = (const __nv_bfloat162 *)&yr, *x2 = (const __nv_bfloat162 *)&xr;
+                    *(uint4 *)(outp + off[u]) = pk[u];
+                    if (want_fwd) {                        // statistics of the values BatchNorm will read (bf16-rounded)
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float2 g = __bfloat1622float2(p2[e]);
-                        const float2 yv = __bfloat1622float2(y2[e]), xv = __bfloat1622float2(x2[e]);
-                        if (p.bn_relu) { if (!(yv.x > 0.f)) g.x = 0.f; if (!(yv.y > 0.f)) g.y = 0.f; }
-                        s0[2 * e] += g.x; s1[2 * e] = fmaf(g.x, (xv.x - mu[2 * e]) * is[2 * e], s1[2 * e]);
-                        s0[2 * e + 1] += g.y; s1[2 * e + 1] = fmaf(g.y, (xv.y - mu[2 * e + 1]) * is[2 * e + 1], s1[2 * e + 1]);
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __bfloat1622float2(p2[e]);
+                            s0[2 * e] += f.x; s1[2 * e] = fmaf(f.x, f.x, s1[2 * e]);
+                            s0[2 * e + 1] += f.y; s1[2 * e + 1] = fmaf(f.y, f.y, s1[2 * e + 1]);
+                        }
+                    } else if (want_bwd) {                 // g = dY*[y>0],  g*xhat  of the BatchNorm that produced this tensor
+                        const __nv_bfloat162 *y2 = (const __nv_bfloat162 *)&yr[u], *x2 = (const __nv_bfloat162 *)&xr[u];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float2 g = __bfloat1622float2(p2[e]);
+                            const float2 yv = __bfloat1622float2(y2[e]), xv = __bfloat1622float2(x2[e]);
+                            if (p.bn_relu) { if (!(yv.x > 0.f)) g.x = 0.f; if (!(yv.y > 0.f)) g.y = 0.f; }
+                            s0[2 * e] += g.x; s1[2 * e] = fmaf(g.x, (xv.x - mu[2 * e]) * is[2 * e], s1[2 * e]);
+                            s0[2 * e + 1] += g.y; s1[2 * e + 1] = fmaf(g.y, (xv.y - mu[2 * e + 1]) * is[2 * e + 1], s1[2 * e + 1]);
+                        }
                     }
                 }
             }
+            if (it == 0 && et == 0) TL(7);
             if (want_fwd || want_bwd) {
                 // lanes with equal (lane % CPR) own the same channels: butterfly over the others, then over the 4 warps
 #pragma unroll
@@ -360,12 +514,15 @@ k_conv(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtens
                 }
             }
             epi_bar();                                     // staging tile and sRed are free again
+            if (it == 0 && et == 0) TL(8);
         }
-        if (p.fuse_bn) {
-            // ---- grid-wide barrier: every CTA of this launch has stored its tiles and contributed its sums
-            __threadfence();
+        if (p.fuse_bn || p.bb_fuse) {
+            // ---- grid-wide barrier: every CTA of this launch has stored its tiles and contributed its sums.
+            // One thread fences (cumulative over the CTA's writes ordered before it by the bar.sync) and arrives.
+            if (et == 0) TL(9);
             epi_bar();
             if (et == 0) {
+                __threadfence();
                 const uint32_t gen = ld_acquire_gpu_u32(p.fb_sync + 1);
                 if (atomicAdd(p.fb_sync, 1u) == gridDim.x - 1) {
                     *(volatile uint32_t *)p.fb_sync = 0u;               // self-resetting: ready for the next launch
@@ -376,12 +533,95 @@ k_conv(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtens
                     while (ld_acquire_gpu_u32(p.fb_sync + 1) == gen)
                         if (clock64() - t0 > 8000000000LL) { *p.fb_err = 1; __threadfence_system(); __trap(); }   // ~4 s: fail loudly
                 }
+                __threadfence();
             }
             epi_bar();
-            // ---- pass 2: y = relu(bn(z) + res) over this CTA's own tiles (z re-read from L2)
+            if (et == 0) TL(10);
+        }
+        if (p.bb_fuse) {
+            // ---- pass 2 (dgrad): BatchNorm backward apply over this CTA's own tiles
+            //      dz = a*g + b*z + k  with  a = gamma*invstd, b = -a*c2*invstd, k = -a*c1 + a*c2*invstd*mean,
+            //      c1 = sum(g)/M, c2 = sum(g*xhat)/M   (same arithmetic as k_bn_bwd_apply_fused)
             int cur_n = -1;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const TileCoord tc = decode_tile<BN_TILE>(p, t);
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const TileCoord tc = decode_work<BN_TILE>(p, w);
+                const TapClass &cls = p.cls[tc.z];
+                if (tc.n != cur_n) {
+                    cur_n = tc.n;
+                    epi_bar();
+                    for (int c = et; c < BN_TILE; c += 128) {
+                        const int ch = tc.ch0 + c;
+                        float sg = 0.f, sgx = 0.f;
+#pragma unroll
+                        for (int k = 0; k < kBnSumCopies; ++k) { sg += __ldcg(p.bn_bsum + (2 * k) * p.out_C + ch); sgx += __ldcg(p.bn_bsum + (2 * k + 1) * p.out_C + ch); }
+                        const float isd = p.bn_invstd[ch], mu_ = p.bn_mean[ch], a = p.bb_gamma[ch] * isd;
+                        const float c1 = sg * p.bb_inv_count, c2 = sgx * p.bb_inv_count;
+                        sSS[c] = -a * c2 * isd;                               // b
+                        sSS[BN_TILE + c] = -a * c1 + a * c2 * isd * mu_;      // k
+                        sRed[c] = a;                                          // a   (sRed is free after the last tile)
+                        if (tc.m == 0 && tc.z == 0 && tc.split == 0) { p.bb_dbeta[ch] = sg; p.bb_dgamma[ch] = sgx; }
+                    }
+                    epi_bar();
+                }
+                float ca[8], cb[8], ck[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { ca[e] = sRed[chunk * 8 + e]; cb[e] = sSS[chunk * 8 + e]; ck[e] = sSS[BN_TILE + chunk * 8 + e]; }
+                const bool staged = !split && tc.t == last_tile;
+#pragma unroll
+                for (int i0 = 0; i0 < CPR; i0 += 4) {
+                    int64_t off[4]; uint4 gr[4], yr[4], xr[4], od[4], orr[4];
+                    bool mine[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u;
+                        const int row = rsub + i * (128 / CPR);
+                        mine[u] = !split || (i & (p.splits - 1)) == tc.split;
+                        off[u] = row_offset(p, tc, row, chunk, cls.oh, cls.ow);
+                        if (mine[u]) {
+                            // dY as stored (after the read-modify-write of phase B): the staging tile only holds this
+                            // launch's own contribution when acc is set, so re-read the stored value in that case
+                            if (staged && !p.acc) gr[u] = *(const uint4 *)(sStage + half * 16384 + row * 128 + ((c8 ^ (row & 7)) << 4));
+                            else gr[u] = __ldcg((const uint4 *)(outp + off[u]));
+                            yr[u] = *(const uint4 *)(p.bn_y + off[u]);
+                            xr[u] = *(const uint4 *)(p.bn_x + off[u]);
+                            if (p.bb_acc_dz) od[u] = *(const uint4 *)(p.bb_dz + off[u]);
+                            if (p.bb_dres && p.bb_acc_dres) orr[u] = *(const uint4 *)(p.bb_dres + off[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (!mine[u]) continue;
+                        const __nv_bfloat162 *g2 = (const __nv_bfloat162 *)&gr[u], *y2 = (const __nv_bfloat162 *)&yr[u], *x2 = (const __nv_bfloat162 *)&xr[u];
+                        const __nv_bfloat162 *d2 = (const __nv_bfloat162 *)&od[u], *q2 = (const __nv_bfloat162 *)&orr[u];
+                        uint4 pz, pr;
+                        __nv_bfloat162 *z2 = (__nv_bfloat162 *)&pz, *r2 = (__nv_bfloat162 *)&pr;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float2 g = __bfloat1622float2(g2[e]);
+                            const float2 yv = __bfloat1622float2(y2[e]), xv = __bfloat1622float2(x2[e]);
+                            if (p.bn_relu) { if (!(yv.x > 0.f)) g.x = 0.f; if (!(yv.y > 0.f)) g.y = 0.f; }
+                            float dx0 = fmaf(ca[2 * e], g.x, fmaf(cb[2 * e], xv.x, ck[2 * e]));
+                            float dx1 = fmaf(ca[2 * e + 1], g.y, fmaf(cb[2 * e + 1], xv.y, ck[2 * e + 1]));
+                            if (p.bb_acc_dz) { const float2 o = __bfloat1622float2(d2[e]); dx0 += o.x; dx1 += o.y; }
+                            z2[e] = __floats2bfloat162_rn(dx0, dx1);
+                            if (p.bb_dres) {
+                                float r0 = g.x, r1 = g.y;
+                                if (p.bb_acc_dres) { const float2 o = __bfloat1622float2(q2[e]); r0 += o.x; r1 += o.y; }
+                                r2[e] = __floats2bfloat162_rn(r0, r1);
+                            }
+                        }
+                        *(uint4 *)(p.bb_dz + off[u]) = pz;
+                        if (p.bb_dres) *(uint4 *)(p.bb_dres + off[u]) = pr;
+                    }
+                }
+            }
+        }
+        if (p.fuse_bn) {
+            // ---- pass 2: y = relu(bn(z) + res) over this CTA's own tiles: the last one is still in the staging
+            // tile, earlier ones are re-read from L2; with split-K every CTA of a tile takes 1/splits of its rows
+            int cur_n = -1;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const TileCoord tc = decode_work<BN_TILE>(p, w);
                 if (tc.n != cur_n) {
                     cur_n = tc.n;
                     epi_bar();
@@ -390,15 +630,16 @@ k_conv(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtens
                         float t0s = 0.f, t1s = 0.f;
 #pragma unroll
                         for (int k = 0; k < kBnSumCopies; ++k) { t0s += __ldcg(p.stats + (2 * k) * p.out_C + ch); t1s += __ldcg(p.stats + (2 * k + 1) * p.out_C + ch); }
-                        const double mean_d = (double)t0s / (double)p.fb_count;
-                        double var_d = (double)t1s / (double)p.fb_count - mean_d * mean_d;
+                        // mean / variance in double (E[x^2] - mean^2 cancels), 1/sqrt in fp32 like torch's fp32 kernels
+                        const double mean_d = (double)t0s * p.fb_inv_count;
+                        double var_d = fma(-mean_d, mean_d, (double)t1s * p.fb_inv_count);
                         if (var_d < 0.0) var_d = 0.0;
                         const float mean = (float)mean_d, var = (float)var_d;
-                        const float istd = (float)(1.0 / sqrt(var_d + (double)p.fb_eps));
+                        const float istd = rsqrtf(var + p.fb_eps);
                         const float g = p.fb_gamma[ch];
                         sSS[c] = istd * g;
                         sSS[BN_TILE + c] = fmaf(-mean, istd * g, p.fb_beta[ch]);
-                        if (tc.m == 0 && tc.z == 0) {                 // exactly one tile per channel block records the statistics
+                        if (tc.m == 0 && tc.z == 0 && tc.split == 0) {        // exactly one work item per channel block records the statistics
                             p.fb_save_mean[ch] = mean; p.fb_save_invstd[ch] = istd;
                             if (p.fb_running_mean) {
                                 const float unbiased = p.fb_count > 1.f ? var * p.fb_count / (p.fb_count - 1.f) : var;
@@ -412,34 +653,49 @@ k_conv(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtens
                 float sc[8], sh[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) { sc[e] = sSS[chunk * 8 + e]; sh[e] = sSS[BN_TILE + chunk * 8 + e]; }
-#pragma unroll 4
-                for (int i = 0; i < CPR; ++i) {
-                    const int row = rsub + i * (128 / CPR);
-                    const int w_l = row & (p.BW - 1);
-                    const int tt = row >> p.lgBW;
-                    const int h_l = tt & (p.BH - 1), n_l = tt >> p.lgBH;
-                    const int64_t off = (((int64_t)(tc.n_blk * p.BN + n_l) * p.out_H + (tc.h_blk * p.BH + h_l)) * p.out_W + w_l) * p.out_C + tc.ch0 + chunk * 8;
-                    const uint4 zr = __ldcg((const uint4 *)(p.out + off));
-                    uint4 rr = make_uint4(0, 0, 0, 0);
-                    if (p.fb_res) rr = *(const uint4 *)(p.fb_res + off);
-                    const __nv_bfloat162 *z2 = (const __nv_bfloat162 *)&zr, *r2 = (const __nv_bfloat162 *)&rr;
-                    uint4 pk;
-                    __nv_bfloat162 *p2 = (__nv_bfloat162 *)&pk;
+                const bool staged = !split && tc.t == last_tile;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 zf = __bfloat1622float2(z2[e]);
-                        float a = fmaf(zf.x, sc[2 * e], sh[2 * e]), b = fmaf(zf.y, sc[2 * e + 1], sh[2 * e + 1]);
-                        if (p.fb_res) { const float2 rf = __bfloat1622float2(r2[e]); a += rf.x; b += rf.y; }
-                        if (p.fb_relu) { a = a > 0.f ? a : 0.f; b = b > 0.f ? b : 0.f; }
-                        p2[e] = __floats2bfloat162_rn(a, b);
+                for (int i0 = 0; i0 < CPR; i0 += 4) {
+                    int64_t off[4]; uint4 zr[4], rr[4];
+                    bool mine[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u;
+                        const int row = rsub + i * (128 / CPR);
+                        mine[u] = !split || (i & (p.splits - 1)) == tc.split;
+                        off[u] = row_offset(p, tc, row, chunk, 0, 0);
+                        rr[u] = make_uint4(0, 0, 0, 0);
+                        if (mine[u]) {
+                            if (staged) zr[u] = *(const uint4 *)(sStage + half * 16384 + row * 128 + ((c8 ^ (row & 7)) << 4));
+                            else zr[u] = __ldcg((const uint4 *)(outp + off[u]));
+                            if (p.fb_res) rr[u] = *(const uint4 *)(p.fb_res + off[u]);
+                        }
                     }
-                    *(uint4 *)(p.fb_y + off) = pk;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (!mine[u]) continue;
+                        const __nv_bfloat162 *z2 = (const __nv_bfloat162 *)&zr[u], *r2 = (const __nv_bfloat162 *)&rr[u];
+                        uint4 pk;
+                        __nv_bfloat162 *p2 = (__nv_bfloat162 *)&pk;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 zf = __bfloat1622float2(z2[e]);
+                            float a = fmaf(zf.x, sc[2 * e], sh[2 * e]), b = fmaf(zf.y, sc[2 * e + 1], sh[2 * e + 1]);
+                            if (p.fb_res) { const float2 rf = __bfloat1622float2(r2[e]); a += rf.x; b += rf.y; }
+                            if (p.fb_relu) { a = a > 0.f ? a : 0.f; b = b > 0.f ? b : 0.f; }
+                            p2[e] = __floats2bfloat162_rn(a, b);
+                        }
+                        *(uint4 *)(p.fb_y + off[u]) = pk;
+                    }
                 }
             }
+            if (et == 0) TL(11);
         }
         tc_fence_before();
     }
     __syncthreads();
+    if (threadIdx.x == 0) TL(12);
+#undef TL
     if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
 }
 
@@ -449,10 +705,11 @@ k_conv(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtens
 constexpr int kStagesWg = 3;
 constexpr int kBoxBytes = 128 * 128;         // [128 pixel rows][64 bf16]
 constexpr int kWgStageBytes = 4 * kBoxBytes; // up to 2 dY boxes + 2 X boxes
-constexpr int kWgSmem = kStagesWg * kWgStageBytes + 1024 + 256;
-constexpr int kWgThreads = 224;              // warps: 0 dY-TMA, 1 MMA, 2..5 epilogue, 6 X-TMA
+constexpr int kWgSmem = kStagesWg * kWgStageBytes + 1024 + 256 + 2 * kStemXsElemsC * 2;
+constexpr int kWgThreads = 224;              // warps: 0 dY-TMA, 1 MMA, 2..5 epilogue, 6 X-TMA  (+ 7..10 gather, stem variant)
 
-__global__ void __launch_bounds__(kWgThreads, 1)
+template <bool STEM>
+__global__ void __launch_bounds__(kWgThreads + (STEM ? kStemExtraThreads : 0), 1)
 k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap dy_map,
         const __grid_constant__ WgradParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -460,6 +717,7 @@ k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUten
     uint64_t *bars = (uint64_t *)(smem + kStagesWg * kWgStageBytes);
     uint64_t *full = bars, *empty = bars + kStagesWg, *tmem_full = bars + 2 * kStagesWg;
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * kStagesWg + 1);
+    bf16 *sXs = (bf16 *)(bars + 2 * kStagesWg + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // N tile: up to two 64-wide K chunks (chunk index over live taps x channel chunks)
@@ -498,9 +756,32 @@ k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUten
                 if (++stage == kStagesWg) { stage = 0; phase ^= 1; }
             }
         }
+    } else if (STEM && warp >= 7) {
+        // ---- stem: the "shifted input" operand is the im2col tile, gathered from the fp32 image (k-chunks chunk0..)
+        const int gt = threadIdx.x - kWgThreads;
+        for (int i = gt; i < 2 * kStemXsElems; i += kStemExtraThreads) sXs[i] = __float2bfloat16_rn(0.f);
+        stem_bar();
+        StemRaw raw;
+        int stage = 0; uint32_t phase = 0, it = 0;
+        if (pt0 < pt1) { stem_load(p.stem_x, pt0 / p.h_blocks, pt0 % p.h_blocks, gt, raw); stem_store(sXs, gt, raw); }
+        stem_bar();
+        for (int pt = pt0; pt < pt1; ++pt, ++it) {
+            const bf16 *xs = sXs + (it & 1) * kStemXsElems;
+            const bool more = pt + 1 < pt1;
+            if (more) stem_load(p.stem_x, (pt + 1) / p.h_blocks, (pt + 1) % p.h_blocks, gt, raw);
+            uint8_t *st = smem + stage * kWgStageBytes;
+            mbar_wait(&empty[stage], phase ^ 1);
+            for (int j = 0; j < nb; ++j) stem_build_chunk(xs, gt, chunk0 + j, st + (2 + j) * kBoxBytes);
+            fence_proxy_async_smem();
+            stem_bar();
+            if (gt == 0) mbar_arrive(&full[stage]);
+            if (++stage == kStagesWg) { stage = 0; phase ^= 1; }
+            if (more) stem_store(sXs + ((it + 1) & 1) * kStemXsElems, gt, raw);
+            stem_bar();
+        }
     } else if (warp == 6) {
         // ---- TMA producer: shifted input boxes
-        if (lane == 0) {
+        if (!STEM && lane == 0) {
             int tap[2], cc[2];
             for (int j = 0; j < nb; ++j) { int c = chunk0 + j; tap[j] = c / p.c_chunks; cc[j] = c - tap[j] * p.c_chunks; }
             int stage = 0; uint32_t phase = 0;
@@ -578,25 +859,44 @@ k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUten
 // =================================================================================
 static std::once_flag g_attr_once;
 static void set_attrs() {
-    cudaFuncSetAttribute(k_conv<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmem);
-    cudaFuncSetAttribute(k_conv<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmem);
-    cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
+    cudaFuncSetAttribute(k_conv<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmem);
+    cudaFuncSetAttribute(k_conv<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmem);
+    cudaFuncSetAttribute(k_conv<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmem);
+    cudaFuncSetAttribute(k_wgrad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
+    cudaFuncSetAttribute(k_wgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
 }
 
-// Output-channel tile: 128 when the 64-wide tiling would need more than one wave of CTAs (halves the
-// activation re-reads and doubles the FLOPs per TMA byte); 64 otherwise (more CTAs, shorter epilogues).
-static int pick_bn_tile(int64_t m_tiles, int channels, int classes) {
-    if (channels % 128 != 0) return 64;
-    return m_tiles * (channels / 64) * classes > (int64_t)umma_num_sms() ? 128 : 64;
+// Tiling heuristic.  Output-channel tile: 128 when the 64-wide tiling would need more than one wave of CTAs (halves the
+// activation re-reads per FLOP); 64 otherwise (more CTAs, shorter epilogues).  Split-K: when the tiles fill less than
+// half of the SMs and K is deep, the k-steps of a tile are divided over 2/4/8 CTAs (>= 6 k-steps each) -- with the
+// 128-wide tile where legal, so that the tile count is small and the split factor large.
+static void pick_tiling(int64_t m_tiles, int channels, int classes, int min_ksteps, int *bn_tile, int *splits) {
+    const int64_t sms = umma_num_sms();
+    *bn_tile = (channels % 128 == 0 && m_tiles * (channels / 64) * classes > sms) ? 128 : 64;
+    *splits = 1;
+    static const bool allow = [] { const char *e = getenv("B2_SPLITK"); return !(e && e[0] == '0'); }();
+    if (!allow || min_ksteps < 12) return;
+    const int bn2 = channels % 128 == 0 ? 128 : 64;
+    const int64_t t2 = m_tiles * (channels / bn2) * classes;
+    int sp = 1;
+    while (t2 * sp * 2 <= sms && min_ksteps / (sp * 2) >= 6 && sp * 2 <= 8) sp *= 2;
+    if (sp > 1) { *bn_tile = bn2; *splits = sp; }
 }
 
-static void finish_plan(UmmaConvPlan *plan, int64_t m_tiles, int channels) {
+static void finish_plan(UmmaConvPlan *plan, int64_t m_tiles, int channels, int splits) {
     ConvParams &p = plan->p;
     p.lgBW = ilog2(p.BW); p.lgBH = ilog2(p.BH);
     p.m_tiles = (int)m_tiles; p.n_tiles = channels / plan->bn_tile;
     p.total_tiles = p.m_tiles * p.n_tiles * p.nclasses;
-    plan->grid = std::min(p.total_tiles, umma_num_sms());
+    p.splits = splits; p.ws = nullptr; p.tile_tickets = nullptr;
+    plan->stem = false;
+    plan->grid = std::min(p.total_tiles * splits, umma_num_sms());
 }
+size_t umma_conv_workspace_floats(const UmmaConvPlan &plan) {
+    return plan.p.splits > 1 ? (size_t)plan.p.total_tiles * 128 * plan.bn_tile : 0;
+}
+size_t umma_conv_ticket_words(const UmmaConvPlan &plan) { return plan.p.splits > 1 ? (size_t)plan.p.total_tiles : 0; }
+void umma_conv_set_workspace(UmmaConvPlan *plan, float *ws, unsigned int *tickets) { plan->p.ws = ws; plan->p.tile_tickets = tickets; }
 
 int umma_plan_fprop(const ConvGeom &g, const bf16 *x, const bf16 *w, bf16 *y, UmmaConvPlan *plan) {
     plan->valid = false;
@@ -617,10 +917,11 @@ int umma_plan_fprop(const ConvGeom &g, const bf16 *x, const bf16 *w, bf16 *y, Um
             c.dh[c.ntaps] = dh; c.dw[c.ntaps] = dw; c.kofs[c.ntaps] = (kh * g.kw + kw) * g.Ci; ++c.ntaps;
         }
     const int64_t m_tiles = (int64_t)(g.N / p.BN) * p.h_blocks;
-    plan->bn_tile = pick_bn_tile(m_tiles, g.Co, 1);
+    int splits = 1;
+    pick_tiling(m_tiles, g.Co, 1, c.ntaps * p.c_chunks, &plan->bn_tile, &splits);
     B2_TRY(make_map_nhwc(&plan->a_map, x, g.N, g.Hi, g.Wi, g.Ci, p.BW, p.BH, p.BN, g.stride));
     B2_TRY(make_map_2d(&plan->b_map, w, g.Co, (int64_t)g.kh * g.kw * g.Ci, plan->bn_tile));
-    finish_plan(plan, m_tiles, g.Co);
+    finish_plan(plan, m_tiles, g.Co, splits);
     plan->flops = 2.0 * g.M() * g.Co * (double)c.ntaps * g.Ci;
     plan->valid = true;
     return 0;
@@ -658,10 +959,12 @@ int umma_plan_dgrad(const ConvGeom &g, const bf16 *dy, const bf16 *w, bf16 *dx, 
             else B2_CHECK(acc || s == 1, B2_ERR_UNSUPPORTED, "umma dgrad: empty parity class needs acc (caller zero-fills)");
         }
     const int64_t m_tiles = (int64_t)(g.N / p.BN) * p.h_blocks;
-    plan->bn_tile = pick_bn_tile(m_tiles, g.Ci, p.nclasses);
+    int splits = 1, min_ksteps = 1 << 30;
+    for (int ci = 0; ci < p.nclasses; ++ci) min_ksteps = std::min(min_ksteps, p.cls[ci].ntaps * p.c_chunks);
+    pick_tiling(m_tiles, g.Ci, p.nclasses, min_ksteps, &plan->bn_tile, &splits);
     B2_TRY(make_map_nhwc(&plan->a_map, dy, g.N, g.Ho, g.Wo, g.Co, p.BW, p.BH, p.BN, 1));
     B2_TRY(make_map_2d(&plan->b_map, w, g.Co, (int64_t)g.kh * g.kw * g.Ci, 64));
-    finish_plan(plan, m_tiles, g.Ci);
+    finish_plan(plan, m_tiles, g.Ci, splits);
     plan->flops = 2.0 * (double)g.N * g.Ho * g.Wo * g.Ci * taps_total * g.Co;
     plan->valid = true;
     return 0;
@@ -670,8 +973,9 @@ int umma_plan_dgrad(const ConvGeom &g, const bf16 *dy, const bf16 *w, bf16 *dx, 
 int umma_conv_check_coresident(const UmmaConvPlan &plan) {
     std::call_once(g_attr_once, set_attrs);
     int per_sm = 0;
-    if (plan.bn_tile == 128) B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_conv<128>, kConvThreads, ConvCfg<128>::kSmem));
-    else B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_conv<64>, kConvThreads, ConvCfg<64>::kSmem));
+    if (plan.stem) B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_conv<64, true>, kConvThreads + kStemExtraThreads, ConvCfg<64>::kSmem));
+    else if (plan.bn_tile == 128) B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_conv<128, false>, kConvThreads, ConvCfg<128>::kSmem));
+    else B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_conv<64, false>, kConvThreads, ConvCfg<64>::kSmem));
     B2_CHECK(per_sm >= 1 && plan.grid <= per_sm * umma_num_sms(), B2_ERR_UNSUPPORTED,
              "fused conv+BatchNorm: grid of %d CTAs is not co-resident (%d per SM x %d SMs)", plan.grid, per_sm, umma_num_sms());
     return 0;
@@ -679,9 +983,13 @@ int umma_conv_check_coresident(const UmmaConvPlan &plan) {
 
 int umma_conv_launch(const UmmaConvPlan &plan, cudaStream_t s) {
     B2_CHECK(plan.valid, B2_ERR_STATE, "umma conv: plan not valid");
+    B2_CHECK(plan.p.splits == 1 || (plan.p.ws && plan.p.tile_tickets), B2_ERR_STATE, "umma conv: split-K plan without workspace");
     std::call_once(g_attr_once, set_attrs);
-    if (plan.bn_tile == 128) { B2_LAUNCH((k_conv<128>), plan.grid, kConvThreads, ConvCfg<128>::kSmem, s, plan.a_map, plan.b_map, plan.p); }
-    else { B2_LAUNCH((k_conv<64>), plan.grid, kConvThreads, ConvCfg<64>::kSmem, s, plan.a_map, plan.b_map, plan.p); }
+    if (plan.stem) {
+        B2_CHECK(plan.p.stem_x && plan.bn_tile == 64 && plan.p.splits == 1, B2_ERR_STATE, "umma conv: stem plan without an input image / unexpected tiling");
+        B2_LAUNCH((k_conv<64, true>), plan.grid, kConvThreads + kStemExtraThreads, ConvCfg<64>::kSmem, s, plan.a_map, plan.b_map, plan.p);
+    } else if (plan.bn_tile == 128) { B2_LAUNCH((k_conv<128, false>), plan.grid, kConvThreads, ConvCfg<128>::kSmem, s, plan.a_map, plan.b_map, plan.p); }
+    else { B2_LAUNCH((k_conv<64, false>), plan.grid, kConvThreads, ConvCfg<64>::kSmem, s, plan.a_map, plan.b_map, plan.p); }
     return 0;
 }
 
@@ -728,6 +1036,7 @@ int umma_plan_wgrad(const ConvGeom &g, const bf16 *x, const bf16 *dy, float *dw,
             }
     plan->need_zero = n < g.kh * g.kw;
     plan->dw = dw;
+    plan->stem = false;
     if (p.splits > 1 && deterministic) {
         B2_CHECK((size_t)p.splits * g.Co * n * g.Ci <= partial_floats, B2_ERR_ARG, "umma wgrad: workspace too small");
         p.out = partial; p.out_pitch = n * g.Ci; p.compact = 1; p.atomic = 0;
@@ -768,7 +1077,12 @@ int umma_wgrad_launch(const UmmaWgradPlan &plan, cudaStream_t s) {
     B2_CHECK(plan.valid, B2_ERR_STATE, "umma wgrad: plan not valid");
     std::call_once(g_attr_once, set_attrs);
     const WgradParams &p = plan.p;
-    B2_LAUNCH(k_wgrad, plan.grid, kWgThreads, kWgSmem, s, plan.x_map, plan.dy_map, plan.p);
+    if (plan.stem) {
+        B2_CHECK(plan.p.stem_x, B2_ERR_STATE, "umma wgrad: stem plan without an input image");
+        B2_LAUNCH(k_wgrad<true>, plan.grid, kWgThreads + kStemExtraThreads, kWgSmem, s, plan.x_map, plan.dy_map, plan.p);
+    } else {
+        B2_LAUNCH(k_wgrad<false>, plan.grid, kWgThreads, kWgSmem, s, plan.x_map, plan.dy_map, plan.p);
+    }
     if (p.splits > 1 && !p.atomic) {
         int64_t n4 = (int64_t)p.Co * p.out_pitch / 4;
         int blocks = (int)ceil_div(n4, 256); if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;

@@ -261,6 +261,11 @@ int Model::finalize() {
             }
         }
     }
+    // classifier head: avgpool immediately followed by its only consumer, the fc layer, and no ReLU in between
+    for (size_t i = 0; i + 1 < ops.size(); ++i)
+        if (ops[i].type == OP_AVGPOOL && ops[i + 1].type == OP_CONV && ops[i + 1].is_fc && ops[i + 1].in == ops[i].out && !ops[i + 1].relu) {
+            ops[i].head_fused = true; ops[i + 1].head_fused = true;
+        }
     // fused BatchNorm: producer conv runs on the tcgen05 path (its epilogue emits the statistics)
     size_t sums_floats = 0;
     std::vector<size_t> sum_off(ops.size(), 0);
@@ -273,6 +278,10 @@ int Model::finalize() {
     }
     size_t sums_off = reserve(sums_floats * 4 + 256);
     size_t err_off = reserve(256);
+    // split-K scratch: a splitting plan has tiles * splits <= #SMs, i.e. at most 74 tiles of 128 x 128 fp32
+    splitk_ws_floats = precision == B2_PREC_BF16 ? (size_t)(kNumSMs / 2) * 128 * 128 : 0;
+    splitk_ticket_words = precision == B2_PREC_BF16 ? 256 : 0;
+    size_t sk_off = reserve(splitk_ws_floats * 4 + 256), skt_off = reserve(splitk_ticket_words * 4 + 256);
     size_t wg_off = reserve(wg_floats * 4 + 256);
     size_t bf_off = precision == B2_PREC_BF16 ? reserve((size_t)n_params * 2 + 256) : 0;
     wgrad_floats = wg_floats;
@@ -297,6 +306,7 @@ int Model::finalize() {
     wgrad_ws = (float *)(base + wg_off);
     bn_sums = (float *)(base + sums_off); bn_sums_bytes = sums_floats * 4;
     fb_err = (int *)(base + err_off);
+    splitk_ws = (float *)(base + sk_off); splitk_tickets = (unsigned int *)(base + skt_off);
     for (size_t i = 0; i < ops.size(); ++i)
         if (ops[i].type == OP_BN && ops[i].bn_fused) {
             ops[i].fsum = bn_sums + sum_off[i]; ops[i].bsum = ops[i].fsum + 2 * (size_t)kBnSumCopies * tensors[ops[i].in].C;
@@ -424,6 +434,7 @@ int Model::time_conv_kernels(int iters, double ms[3], double flops[3], int launc
     };
     for (Op &o : ops) {
         if (o.type != OP_CONV || !(o.use_umma || o.stem_umma)) continue;
+        if (o.stem_umma && o.stem_gather) { B2_CHECK(cur_x, B2_ERR_STATE, "time_conv_kernels: no input image yet"); o.fplan.p.stem_x = cur_x; o.wplan.p.stem_x = cur_x; }
         B2_TRY(timed(0, o.fplan.flops, [&] { return umma_conv_launch(o.fplan, s); }));
         if (o.use_umma && o.need_dgrad) B2_TRY(timed(1, o.dplan.flops, [&] { return umma_conv_launch(o.dplan, s); }));
         B2_TRY(timed(2, o.wplan.flops, [&] { return umma_wgrad_launch(o.wplan, s); }));
@@ -453,8 +464,13 @@ int Model::build_plans() {
         if (o.type == OP_CONV && o.stem_umma) {
             Tensor &to = tensors[o.out];
             B2_TRY(umma_plan_fprop(o.vg, o.col, o.wpad, (bf16 *)to.val, &o.fplan));
+            // gather the im2col rows in shared memory straight from the fp32 image (no 50 MB im2col round trip)
+            static const bool gather = [] { const char *e = getenv("B2_STEM_GATHER"); return !(e && e[0] == '0'); }();
+            o.stem_gather = gather && umma_stem_supported(o.g, o.vg, o.kpad) && o.fplan.bn_tile == 64 && o.fplan.p.splits == 1;
+            o.fplan.stem = o.stem_gather;
             B2_TRY(umma_plan_wgrad(o.vg, o.col, (const bf16 *)to.grad, o.dwpad, wgrad_ws, wgrad_floats, deterministic, &o.wplan));
             if (o.wplan.p.atomic) zero_grads_each_step = true;
+            o.wplan.stem = o.stem_gather;
             continue;
         }
         if (o.type != OP_CONV || !o.use_umma) continue;
@@ -471,6 +487,15 @@ int Model::build_plans() {
         B2_TRY(umma_wgrad_zero_dead(o.wplan, 0));      // once: dead-tap gradients are exactly zero and never rewritten
     }
     B2_CUDA(cudaStreamSynchronize(0));
+    for (Op &o : ops) {
+        if (o.type != OP_CONV || !(o.use_umma || o.stem_umma)) continue;
+        for (UmmaConvPlan *pl : {&o.fplan, &o.dplan}) {
+            if (!pl->valid || pl->p.splits == 1) continue;
+            B2_CHECK(umma_conv_workspace_floats(*pl) <= splitk_ws_floats && umma_conv_ticket_words(*pl) <= splitk_ticket_words, B2_ERR_STATE,
+                     "split-K workspace too small (%zu floats needed)", umma_conv_workspace_floats(*pl));
+            umma_conv_set_workspace(pl, splitk_ws, splitk_tickets);
+        }
+    }
     for (Op &b : ops) {
         if (b.type != OP_BN || !b.bn_fused) continue;
         b.fwd_in_conv = false;
@@ -491,13 +516,13 @@ int Model::build_plans() {
                     q.fb_running_mean = p_buffers ? p_buffers + b.rm_off : nullptr;
                     q.fb_running_var = p_buffers ? p_buffers + b.rv_off : nullptr;
                     q.fb_sync = b.fb_counter; q.fb_err = fb_err;
-                    q.fb_count = (float)((int64_t)tx.N * tx.H * tx.W); q.fb_eps = 1e-5f; q.fb_momentum = 0.1f;
+                    q.fb_count = (float)((int64_t)tx.N * tx.H * tx.W); q.fb_inv_count = 1.0 / (double)((int64_t)tx.N * tx.H * tx.W); q.fb_eps = 1e-5f; q.fb_momentum = 0.1f;
                     q.fb_relu = b.relu ? 1 : 0;
                     b.fwd_in_conv = true;
                 }
             }
         // last writer of d(b.out) in backward order = its first consumer in forward order
-        b.bwd_sums_fused = false;
+        b.bwd_sums_fused = false; b.bwd_apply_fused = false;
         for (Op &c : ops) {
             bool consumes = (c.in == b.out) || (c.res == b.out);
             if (!consumes) continue;
@@ -510,6 +535,18 @@ int Model::build_plans() {
                 q.bn_bsum = b.bsum; q.bn_x = (const bf16 *)tensors[b.in].val; q.bn_y = (const bf16 *)tensors[b.out].val;
                 q.bn_mean = b.bn.mean; q.bn_invstd = b.bn.invstd; q.bn_relu = b.relu ? 1 : 0;
                 b.bwd_sums_fused = true;
+                // ... and the apply as well, behind the same kind of grid barrier the forward fusion uses
+                static const bool fuse_apply = [] { const char *e = getenv("B2_FUSE_BN_APPLY"); return !(e && e[0] == '0'); }();
+                if (fuse_apply && umma_conv_check_coresident(c.dplan) == 0) {
+                    const Tensor &tz = tensors[b.in];
+                    q.bb_fuse = 1;
+                    q.bb_dz = (bf16 *)tz.grad; q.bb_dres = b.res >= 0 ? (bf16 *)tensors[b.res].grad : nullptr;
+                    q.bb_acc_dz = b.acc_in ? 1 : 0; q.bb_acc_dres = b.acc_res ? 1 : 0;
+                    q.bb_gamma = p_params + b.w_off; q.bb_dgamma = p_grads + b.w_off; q.bb_dbeta = p_grads + b.b_off;
+                    q.bb_inv_count = 1.f / (float)((int64_t)tz.N * tz.H * tz.W);
+                    q.fb_sync = b.fb_counter + 2; q.fb_err = fb_err;
+                    b.bwd_apply_fused = true;
+                }
             }
             break;      // only the first consumer matters
         }
@@ -531,7 +568,13 @@ int Model::run_graphed(std::vector<GraphEntry> &cache, const void *a, const void
             g_launches += g.launches;
             return 0;
         }
-    if (!cap_stream) B2_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+    if (!cap_stream) {
+        // the forward / backward main path is captured on a HIGH-priority stream: its kernel nodes then win the SMs
+        // that free up over the concurrently running weight-gradient / optimizer branches (default priority)
+        int lo = 0, hi = 0;
+        B2_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        B2_CUDA(cudaStreamCreateWithPriority(&cap_stream, cudaStreamNonBlocking, hi));
+    }
     if (cache.size() >= 8) { cudaGraphExecDestroy(cache.front().exec); cache.erase(cache.begin()); }
     const int64_t l0 = g_launches;
     B2_CUDA(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
@@ -611,7 +654,8 @@ int Model::forward_impl(const float *x_nchw, float *logits, cudaStream_t s) {
             Tensor &ti = tensors[o.in];
             if (o.stem_umma) {
                 int ph = prof_begin(PC_CONV_FPROP, 2.0 * o.g.M() * o.g.Co * o.g.K(), (double)o.vg.M() * o.kpad * 4 + to.numel * 2.0, s);
-                B2_TRY(op_stem_im2col(cur_x, o.col, o.g.N, o.g.Ci, o.g.Hi, o.g.Wi, o.g.kh, o.g.stride, o.g.pad, o.g.Ho, o.g.Wo, o.kpad, s));
+                if (o.stem_gather) o.fplan.p.stem_x = cur_x;
+                else B2_TRY(op_stem_im2col(cur_x, o.col, o.g.N, o.g.Ci, o.g.Hi, o.g.Wi, o.g.kh, o.g.stride, o.g.pad, o.g.Ho, o.g.Wo, o.kpad, s));
                 B2_TRY(op_stem_pack_weights(p_params + o.w_off, o.wpad, o.g.Co, o.g.Ci, o.g.kh, o.kpad, s));
                 B2_TRY(umma_conv_launch(o.fplan, s));
                 prof_end(ph, s);
@@ -619,6 +663,12 @@ int Model::forward_impl(const float *x_nchw, float *logits, cudaStream_t s) {
             }
             if (o.is_fc) {
                 int ph = prof_begin(PC_OTHER, 0, 0, s);
+                if (o.head_fused) {          // avgpool + fc in one kernel (the avgpool op before this one was skipped)
+                    const Op &ap = ops[&o - &ops[0] - 1];
+                    const Tensor &tp = tensors[ap.in];
+                    B2_TRY(op_head_forward(tp.val, tp.dt, p_params + o.w_off, o.b_off >= 0 ? p_params + o.b_off : nullptr, (float *)ti.val,
+                                           (float *)to.val, tp.N, tp.H * tp.W, tp.C, o.g.Co, s));
+                } else
                 B2_TRY(op_fc_forward((const float *)ti.val, p_params + o.w_off, o.b_off >= 0 ? p_params + o.b_off : nullptr,
                                      (float *)to.val, o.g.N, o.g.Ci, o.g.Co, o.relu, s));
                 prof_end(ph, s);
@@ -666,6 +716,7 @@ int Model::forward_impl(const float *x_nchw, float *logits, cudaStream_t s) {
             break;
         }
         case OP_AVGPOOL: {
+            if (o.head_fused) break;         // done by the fc op's fused kernel
             Tensor &ti = tensors[o.in];
             B2_TRY(op_avgpool_forward(ti.val, ti.dt, (float *)to.val, ti.N, ti.H * ti.W, ti.C, s));
             break;
@@ -679,7 +730,8 @@ int Model::forward_impl(const float *x_nchw, float *logits, cudaStream_t s) {
 int Model::backward(const float *dlogits, cudaStream_t s) {
     B2_CHECK(device >= 0 && slab, B2_ERR_STATE, "model: metadata-only instance (created with device < 0) cannot execute");
     B2_CHECK(p_params && p_grads, B2_ERR_STATE, "model: parameters/gradients not bound (b2_model_bind)");
-    if (use_graphs && !profiling && eager_runs_bwd >= 2) return run_graphed(bwd_graphs, dlogits, nullptr, false, s);
+    // the stem's weight gradient gathers from the input image of the matching forward: part of the graph key
+    if (use_graphs && !profiling && eager_runs_bwd >= 2) return run_graphed(bwd_graphs, dlogits, cur_x, false, s);
     ++eager_runs_bwd;
     return backward_impl(dlogits, s);
 }
@@ -738,12 +790,25 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
             if (o.stem_umma) {
                 int ph = prof_begin(PC_CONV_WGRAD, 2.0 * o.g.M() * o.g.Co * o.g.K(), (double)o.vg.M() * o.kpad * 2 + to.numel * 2.0, s);
                 cudaStream_t ws = wgrad_stream();
+                if (o.stem_gather) o.wplan.p.stem_x = cur_x;
                 B2_TRY(umma_wgrad_launch(o.wplan, ws));
                 B2_TRY(op_stem_unpack_wgrad(o.dwpad, p_grads + o.w_off, o.g.Co, o.g.Ci, o.g.kh, o.kpad, ws));
                 prof_end(ph, s);
                 break;
             }
             if (o.relu) B2_TRY(op_relu_mask(to.val, to.grad, to.dt, to.numel, s));
+            if (o.is_fc && o.head_fused) {
+                // weight gradient off the critical path; dgrad + average-pool backward in one kernel
+                int ph = prof_begin(PC_OTHER, 0, 0, s);
+                B2_TRY(op_fc_wgrad((const float *)ti.val, (const float *)to.grad, p_grads + o.w_off, o.b_off >= 0 ? p_grads + o.b_off : nullptr,
+                                   o.g.N, o.g.Ci, o.g.Co, wgrad_stream()));
+                const Op &ap = ops[i - 1];
+                Tensor &tp = tensors[ap.in];
+                B2_TRY(op_head_dgrad(p_params + o.w_off, (const float *)to.grad, (float *)ti.grad, tp.grad, tp.dt, tp.N, tp.H * tp.W, tp.C,
+                                     o.g.Co, ap.acc_in, s));
+                prof_end(ph, s);
+                break;
+            }
             if (o.is_fc) {
                 int ph = prof_begin(PC_OTHER, 0, 0, s);
                 B2_TRY(op_fc_backward((const float *)ti.val, p_params + o.w_off, (const float *)to.grad, p_grads + o.w_off,
@@ -778,12 +843,13 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
             break;
         }
         case OP_BN: {
+            if (o.bn_fused && o.bwd_apply_fused) break;      // done inside the dgrad kernel that finalised d(o.out)
             int64_t M = (int64_t)ti.N * ti.H * ti.W;
             int ph = prof_begin(PC_BN_BWD, 0, ti.numel * (double)dt_size(ti.dt) * (o.res >= 0 ? 7.0 : 6.0), s);
             if (o.bn_fused)
                 B2_TRY(op_bn_backward_fused(ti.val, to.val, to.grad, ti.grad, o.res >= 0 ? tensors[o.res].grad : nullptr, ti.dt, M,
                                             ti.C, o.bsum, p_params + o.w_off, p_grads + o.w_off, p_grads + o.b_off, o.relu,
-                                            o.acc_in, o.acc_res, o.bwd_sums_fused, o.bn, s));
+                                            o.acc_in, o.acc_res, o.bwd_sums_fused || o.pool_sums_ready, o.bn, s));
             else
             B2_TRY(op_bn_backward(ti.val, to.val, to.grad, ti.grad, o.res >= 0 ? tensors[o.res].grad : nullptr, ti.dt, M,
                                   ti.C, p_params + o.w_off, p_grads + o.w_off, p_grads + o.b_off, o.relu, o.acc_in,
@@ -793,6 +859,19 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
         }
         case OP_MAXPOOL:
             if (o.need_dgrad) {
+                // the pool's input is the output of a fused BatchNorm (the stem): produce that BatchNorm's backward sums
+                // in the same pass -- the BN op that follows in this loop then only runs its apply kernel
+                Op *pb = nullptr;
+                for (Op &b : ops) if (b.type == OP_BN && b.out == o.in && b.bn_fused && !b.bwd_sums_fused) pb = &b;
+                static const bool fuse_pool = [] { const char *e = getenv("B2_FUSE_POOL_BN"); return !(e && e[0] == '0'); }();
+                bool sole = true;
+                for (const Op &c : ops) if (&c != &o && (c.in == o.in || c.res == o.in)) sole = false;      // pool is the only consumer
+                if (fuse_pool && pb && sole && ti.dt == DT_BF16 && !o.out_nchw && o.g.Ci % 8 == 0 && 256 % (o.g.Ci / 8) == 0) {
+                    B2_TRY(op_maxpool_backward_bn_reduce((const bf16 *)to.grad, o.idx, (bf16 *)ti.grad, (const bf16 *)ti.val,
+                                                         (const bf16 *)tensors[pb->in].val, pb->bn.mean, pb->bn.invstd, pb->bsum, o.g.N, o.g.Hi,
+                                                         o.g.Wi, o.g.Ci, o.g.kh, o.g.stride, o.g.pad, o.g.Ho, o.g.Wo, o.acc_in, pb->relu, s));
+                    pb->pool_sums_ready = true;
+                } else
                 if (ti.dt == DT_BF16 && !o.out_nchw && o.g.Ci % 8 == 0)
                     B2_TRY(op_maxpool_backward_bf16x8((const bf16 *)to.grad, o.idx, (bf16 *)ti.grad, o.g.N, o.g.Hi, o.g.Wi, o.g.Ci,
                                                       o.g.kh, o.g.stride, o.g.pad, o.g.Ho, o.g.Wo, o.acc_in, s));
@@ -802,6 +881,7 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
             }
             break;
         case OP_AVGPOOL:
+            if (o.head_fused) break;         // done by the fc op's fused dgrad kernel
             B2_TRY(op_avgpool_backward((const float *)to.grad, ti.grad, ti.dt, ti.N, ti.H * ti.W, ti.C, o.acc_in, s));
             break;
         }

@@ -58,6 +58,11 @@ int op_maxpool_forward_bf16x8(const bf16 *x, bf16 *y, uint8_t *idx, int N, int H
 int op_maxpool_backward_bf16x8(const bf16 *dy, const uint8_t *idx, bf16 *dx, int N, int Hi, int Wi, int C, int k,
                                int stride, int pad, int Ho, int Wo, bool acc, cudaStream_t s);
 
+// max-pool backward + the BatchNorm-backward sums of the BatchNorm whose output feeds the pool (stem), one pass
+int op_maxpool_backward_bn_reduce(const bf16 *dy, const uint8_t *idx, bf16 *dx, const bf16 *y, const bf16 *z, const float *mean,
+                                  const float *invstd, float *bsum, int N, int Hi, int Wi, int C, int k, int stride, int pad, int Ho, int Wo,
+                                  bool acc, bool relu, cudaStream_t s);
+
 // ---- stem: fp32 NCHW image -> bf16 im2col rows [N*Ho*Wo][kpad] for a k x k / stride / pad conv,
 // column order (kh, kw, c) = the O,H,W,I weight order; columns >= k*k*C are zero
 int op_stem_im2col(const float *x_nchw, bf16 *col, int N, int C, int H, int W, int k, int stride, int pad, int Ho,
@@ -73,6 +78,12 @@ int op_fc_forward(const float *x, const float *w, const float *bias, float *y, i
 // dw [N][K], db [N] (may be null), dx [B][K] (may be null; acc adds)
 int op_fc_backward(const float *x, const float *w, const float *dy, float *dw, float *db, float *dx, int B, int K, int N,
                    bool acc_dx, cudaStream_t s);
+
+// fused head: feat = mean over HW of x (written, fp32 [B][C]); y = feat W^T + bias  /  dfeat = dy W (written), dx (+)= dfeat / HW
+int op_head_forward(const void *x, int xdt, const float *w, const float *bias, float *feat, float *y, int B, int HW, int C, int N,
+                    cudaStream_t s);
+int op_head_dgrad(const float *w, const float *dy, float *dfeat, void *dx, int xdt, int B, int HW, int C, int N, bool acc, cudaStream_t s);
+int op_fc_wgrad(const float *x, const float *dy, float *dw, float *db, int B, int K, int N, cudaStream_t s);
 
 // ---- pointwise ------------------------------------------------------------------
 // dy = y > 0 ? dy : 0  (in place)

@@ -78,6 +78,117 @@ class _CommBuffer:
         return buf.raw
 
 
+class _VmmBuffer:
+    """A cuMemCreate allocation (shareable as a POSIX file descriptor, bindable to an NVSwitch multicast object)
+    viewed as a flat fp32 torch tensor.  ``n_floats`` is rounded up to the allocation granularity."""
+
+    def __init__(self, n_floats: int, device: torch.device, granularity: int):
+        self.bytes = (n_floats * 4 + granularity - 1) // granularity * granularity
+        p, h, fd = C.c_void_p(), C.c_int64(), C.c_int()
+        call("b2_vmm_alloc", device.index, self.bytes, C.byref(p), C.byref(h), C.byref(fd))
+        self.ptr, self.handle, self.fd, self.n = p.value, h.value, fd.value, n_floats
+        self.tensor = _as_tensor(self.ptr, n_floats, device, self)
+
+
+def _exchange_fds(my_fds: List[int], root: Optional[int] = None) -> List[List[int]]:
+    """File descriptors cannot travel through gloo: pass them over Unix-domain sockets (SCM_RIGHTS).
+    root=None: all-to-all (returns, per rank, that rank's descriptors as valid in THIS process; own entry = my_fds);
+    root=r: only rank r sends (returns [fds of r] at index r)."""
+    import socket
+    import torch.distributed as dist
+    W, r = _state["world"], _state["rank"]
+    base = f"/tmp/b2ddp.{os.environ.get('MASTER_PORT', '0')}.{os.getppid()}"
+    path = f"{base}.{r}.sock"
+    if os.path.exists(path):
+        os.unlink(path)
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(path)
+    srv.listen(W + 1)
+    dist.barrier()                                        # every listener exists
+    paths = [None] * W
+    dist.all_gather_object(paths, path)
+    senders = range(W) if root is None else [root]
+    if r in senders:
+        for q in range(W):
+            if q == r:
+                continue
+            c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            c.connect(paths[q])
+            socket.send_fds(c, [r.to_bytes(4, "little")], list(my_fds))
+            c.close()
+    out: List[List[int]] = [[] for _ in range(W)]
+    if r in senders:
+        out[r] = list(my_fds)
+    expect = len([q for q in senders if q != r])
+    for _ in range(expect):
+        conn, _ = srv.accept()
+        msg, fds, _, _ = socket.recv_fds(conn, 16, 16)
+        out[int.from_bytes(msg[:4], "little")] = list(fds)
+        conn.close()
+    dist.barrier()
+    srv.close()
+    os.unlink(path)
+    return out
+
+
+def _nvls_available(dev: torch.device, want: Optional[bool]):
+    """(every rank can bind multicast memory, allocation granularity)."""
+    W = _state["world"]
+    mc_ok, gran = C.c_int(0), C.c_int64(0)
+    want = want if want is not None else os.environ.get("B2_NVLS", "1") != "0"
+    ok = False
+    if want and W > 1:
+        try:
+            call("b2_vmm_query", dev.index, C.byref(mc_ok), C.byref(gran))
+            ok = bool(mc_ok.value)
+        except B2Error:
+            ok = False
+    return all(_exchange(ok)), gran.value
+
+
+def _share_vmm(bufs: List["_VmmBuffer"], dev: torch.device):
+    """Map every peer's copy of each buffer in ``bufs`` and bind each buffer to a multicast object.
+    Returns (ptrs[k][q] = address of rank q's buffer k in this process, mc[k] = multicast address of buffer k)."""
+    W, r = _state["world"], _state["rank"]
+    K = len(bufs)
+    ptrs = [[None] * W for _ in range(K)]
+    fds = _exchange_fds([b.fd for b in bufs])
+    for k, buf in enumerate(bufs):
+        ptrs[k][r] = buf.ptr
+        for q in range(W):
+            if q == r:
+                continue
+            out = C.c_void_p()
+            call("b2_vmm_import", dev.index, fds[q][k], buf.bytes, C.byref(out))
+            lib().b2_vmm_close_fd(fds[q][k])
+            ptrs[k][q] = out.value
+    # one multicast object per buffer: rank 0 creates, everybody adds its device, then binds + maps
+    mch = [C.c_int64() for _ in range(K)]
+    if r == 0:
+        mfd = [C.c_int() for _ in range(K)]
+        for k, buf in enumerate(bufs):
+            call("b2_mc_create", W, buf.bytes, C.byref(mch[k]), C.byref(mfd[k]))
+        _exchange_fds([m.value for m in mfd], root=0)
+        for m in mfd:
+            lib().b2_vmm_close_fd(m.value)
+    else:
+        got = _exchange_fds([], root=0)
+        for k in range(K):
+            call("b2_mc_import", got[0][k], C.byref(mch[k]))
+            lib().b2_vmm_close_fd(got[0][k])
+    for k in range(K):
+        call("b2_mc_add_device", mch[k].value, dev.index)
+    _exchange("mc-added")                          # binding requires ALL devices to have been added
+    mc = []
+    for k, buf in enumerate(bufs):
+        out = C.c_void_p()
+        call("b2_mc_bind_and_map", mch[k].value, buf.handle, buf.bytes, dev.index, C.byref(out))
+        mc.append(out.value)
+        lib().b2_vmm_close_fd(buf.fd)
+    _exchange("mc-bound")
+    return ptrs, mc
+
+
 class _Holder:
     def __init__(self, ptr, n, owner):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
@@ -107,7 +218,7 @@ class DistributedDataParallel:
     """
 
     def __init__(self, module, device_ids: Optional[List[int]] = None, algo: int = 0, overlap: bool = True,
-                 bucket_cap_mb: float = 32.0):
+                 bucket_cap_mb: float = 4.0, nvls: Optional[bool] = None):
         if not _state["distributed"]:
             raise B2Error("Default process group has not been initialized: call init_distributed(args) "
                           "under torchrun first (cifar_example_ddp.py:69)")
@@ -130,30 +241,47 @@ class DistributedDataParallel:
         W, r = _state["world"], _state["rank"]
         dev = e.device
         npad = max((e.n_params + 3) // 4 * 4, 4)
-        self._grads = _CommBuffer(npad, dev)
-        self._params = _CommBuffer(npad, dev)
+        # NVLS (in-switch reduction) needs cuMemCreate memory bound to a multicast object; otherwise cudaMalloc + IPC
+        self.nvls, gran = _nvls_available(dev, nvls)
+        if self.nvls:
+            self._grads = _VmmBuffer(npad, dev, gran)
+            self._params = _VmmBuffer(npad, dev, gran)
+        else:
+            self._grads = _CommBuffer(npad, dev)
+            self._params = _CommBuffer(npad, dev)
         self._bufs = _CommBuffer(max((e.n_buffers + 3) // 4 * 4, 4), dev)
         self._flags = _CommBuffer(lib().b2_comm_flag_bytes() // 4, dev)
         bufs = iter([self._params, self._grads, self._bufs])
         e._allocate(lambda n: next(bufs).tensor[:n])
         e._keep.append(self)
         # ---- exchange IPC handles, map peers
-        handles = _exchange((self._grads.handle(), self._params.handle(), self._flags.handle(), self._bufs.handle()))
         self._peer_ptrs = []
-        g, p, f, b = [], [], [], []
-        for q in range(W):
-            if q == r:
-                g.append(self._grads.ptr); p.append(self._params.ptr); f.append(self._flags.ptr); b.append(self._bufs.ptr)
-                continue
-            ptrs = []
-            for h in handles[q]:
-                out = C.c_void_p()
-                call("b2_comm_import", h, C.byref(out))
-                ptrs.append(out.value)
-            self._peer_ptrs.extend(ptrs)
-            g.append(ptrs[0]); p.append(ptrs[1]); f.append(ptrs[2]); b.append(ptrs[3])
+        g, p, f, b = [None] * W, [None] * W, [None] * W, [None] * W
+        g[r], p[r], f[r], b[r] = self._grads.ptr, self._params.ptr, self._flags.ptr, self._bufs.ptr
+
+        def import_ipc(h):
+            out = C.c_void_p()
+            call("b2_comm_import", h, C.byref(out))
+            self._peer_ptrs.append(out.value)
+            return out.value
+
+        mc_ptrs = None
+        if self.nvls:
+            ptrs, mc_ptrs = _share_vmm([self._grads, self._params], dev)
+            g, p = ptrs[0], ptrs[1]
+            handles = _exchange((self._flags.handle(), self._bufs.handle()))
+            for q in range(W):
+                if q != r:
+                    f[q], b[q] = import_ipc(handles[q][0]), import_ipc(handles[q][1])
+        else:
+            handles = _exchange((self._grads.handle(), self._params.handle(), self._flags.handle(), self._bufs.handle()))
+            for q in range(W):
+                if q != r:
+                    g[q], p[q], f[q], b[q] = (import_ipc(h) for h in handles[q])
         arr = lambda xs: (C.c_void_p * W)(*xs)
         call("b2_comm_register", arr(g), arr(p), arr(f), npad)
+        if mc_ptrs is not None:
+            call("b2_comm_register_multicast", C.c_void_p(mc_ptrs[0]), C.c_void_p(mc_ptrs[1]))
         # ---- rank 0's parameters and buffers win (distributed.py:883-890)
         torch.cuda.synchronize(dev)
         _exchange("params-ready")
@@ -268,6 +396,7 @@ def destroy() -> None:
             w._close_peers()
         _wrappers.clear()
         call("b2_comm_finalize")               # frees this rank's buffers: wrapped models are dead after this
+        lib().b2_vmm_release_all()
         _state["comm"] = False
     if _state["pg"]:
         import torch.distributed as dist

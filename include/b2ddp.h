@@ -130,11 +130,12 @@ int b2_conv_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, int p
                  const void *dy_bf16, void *out, void *stream);
 /* one fprop launch with the fused BatchNorm(+residual, ReLU) epilogue, exactly as the model issues it for
  * every conv+BN pair (torchvision resnet.py:92-94: conv -> bn -> relu): z = conv(x), y = relu?(bn_train(z) + res).
- * info3 (optional) returns {output-channel tile, persistent grid, tile count}. */
+ * info3 (optional) returns {output-channel tile, persistent grid, tile count}; timeline13 (optional, host) returns
+ * clock64() of CTA 0 at 13 points of the kernel (setup, first data, last MMA, epilogue phases, grid barrier, ...). */
 int b2_conv_bn_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, int pad, int relu,
                     const void *x_bf16, const float *w_master, const void *res_bf16, const float *gamma,
                     const float *beta, void *z_out, void *y_out, float *mean_out, float *invstd_out,
-                    int *info3, void *stream);
+                    int *info3, long long *timeline13, void *stream);
 
 /* ---- next rows: input transform and eval counters -----------------------------
  * transforms.ToTensor() + Normalize(mean, std) (cifar_example_ddp.py:61-63) on the device:
@@ -182,6 +183,26 @@ int b2_comm_register(void *const *grads, void *const *params, void *const *flags
 /* dist.barrier() (cifar_example_ddp.py:58): flag barrier in peer memory */
 int b2_comm_barrier(void *stream);
 /* size in bytes of one rank's flag pad (== B2_FLAG_WORDS * 4) */
+/* ---- NVLS (in-switch reduction) support: VMM allocations + multicast objects --------------------------------
+ * Replaces what NCCL sets up for the NVLS all-reduce behind cifar_example_ddp.py:57,83,106.  Host protocol
+ * (parallel.py): every rank b2_vmm_alloc()s its gradient / parameter vectors, sends the file descriptors to its
+ * peers over Unix sockets, b2_vmm_import()s theirs (plain peer pointers); rank 0 b2_mc_create()s one multicast
+ * object per vector and distributes its descriptor; every rank b2_mc_import()s (rank 0 keeps its handle),
+ * b2_mc_add_device()s, and -- once ALL ranks have added -- b2_mc_bind_and_map()s; the resulting multicast
+ * addresses go to b2_comm_register_multicast().  Falls back to the peer load/store kernels when
+ * b2_vmm_query() reports no multicast support. */
+int b2_vmm_query(int device, int *multicast_supported, int64_t *granularity);
+int b2_vmm_alloc(int device, int64_t bytes, void **ptr, int64_t *handle_out, int *fd_out);
+int b2_vmm_import(int device, int fd, int64_t bytes, void **peer_ptr);
+int b2_mc_create(int world, int64_t bytes, int64_t *mc_handle, int *fd_out);
+int b2_mc_import(int fd, int64_t *mc_handle);
+int b2_mc_add_device(int64_t mc_handle, int device);
+int b2_mc_bind_and_map(int64_t mc_handle, int64_t mem_handle, int64_t bytes, int device, void **mc_ptr);
+int b2_vmm_close_fd(int fd);
+int b2_vmm_release_all(void);
+int b2_comm_register_multicast(void *mc_grads, void *mc_params);
+int b2_comm_set_nvls(int enable);
+int b2_comm_nvls_active(void);
 int b2_comm_flag_bytes(void);
 /* synchronises the device and reports B2_ERR_TIMEOUT if any comm kernel gave up waiting
  * for a peer flag (a rank died or the ranks' launch sequences diverged) */

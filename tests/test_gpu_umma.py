@@ -138,7 +138,7 @@ def test_fprop_fused_batchnorm(shape, relu, with_res):
     mean, invstd = torch.zeros(Co, device=DEV), torch.zeros(Co, device=DEV)
     info = (C.c_int * 3)()
     b2._lib.call("b2_conv_bn_test", N, Hi, Wi, Ci, Co, k, s, p, relu, _vp(x), _vp(w), _vp(res), _vp(gamma), _vp(beta), _vp(z), _vp(y),
-                 _vp(mean), _vp(invstd), info, None)
+                 _vp(mean), _vp(invstd), info, None, None)
     zr = F.conv2d(x.float().permute(0, 3, 1, 2), w.bfloat16().float().permute(0, 3, 1, 2), stride=s, padding=p)
     zs = zr.abs().max().item()
     assert (z.float().permute(0, 3, 1, 2) - zr).abs().max().item() < 1e-2 * zs
