@@ -272,20 +272,8 @@ int b2_conv_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, int p
     if (rc == 0) {
         if (use_umma) {
             if (!umma_conv_eligible(g)) { set_error("conv_test: shape not eligible for the tcgen05 path"); rc = B2_ERR_UNSUPPORTED; }
-            else if (mode == 0 || mode == 1) {
-                UmmaConvPlan pl;
-                rc = mode == 0 ? umma_plan_fprop(g, (const bf16 *)x_bf16, w, (bf16 *)out, &pl)
-                               : umma_plan_dgrad(g, (const bf16 *)dy_bf16, w, (bf16 *)out, acc != 0, &pl);
-                float *skw = nullptr;
-                if (!rc && pl.p.splits > 1) {
-                    const size_t nf = umma_conv_workspace_floats(pl) + umma_conv_ticket_words(pl);
-                    if (cudaMalloc(&skw, nf * 4) != cudaSuccess || cudaMemsetAsync(skw, 0, nf * 4, s) != cudaSuccess) rc = B2_ERR_CUDA;
-                    else umma_conv_set_workspace(&pl, skw, (unsigned int *)(skw + umma_conv_workspace_floats(pl)));
-                }
-                if (!rc) rc = umma_conv_launch(pl, s);
-                cudaStreamSynchronize(s);
-                cudaFree(skw);
-            }
+            else if (mode == 0) { UmmaConvPlan pl; rc = umma_plan_fprop(g, (const bf16 *)x_bf16, w, (bf16 *)out, &pl); if (!rc) rc = umma_conv_launch(pl, s); }
+            else if (mode == 1) { UmmaConvPlan pl; rc = umma_plan_dgrad(g, (const bf16 *)dy_bf16, w, (bf16 *)out, acc != 0, &pl); if (!rc) rc = umma_conv_launch(pl, s); }
             else {
                 UmmaWgradPlan pl; rc = umma_plan_wgrad(g, (const bf16 *)x_bf16, (const bf16 *)dy_bf16, (float *)out, ws, wsf, acc != 0 /* deterministic */, &pl);
                 if (!rc && (pl.p.atomic || pl.need_zero)) { cudaError_t ze = cudaMemsetAsync(out, 0, (size_t)Co * taps * Ci * 4, s); if (ze != cudaSuccess) rc = B2_ERR_CUDA; }
@@ -327,12 +315,6 @@ int b2_conv_bn_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, in
     UmmaConvPlan pl;
     if (!rc) rc = umma_plan_fprop(g, (const bf16 *)x_bf16, w, (bf16 *)z_out, &pl);
     if (!rc) rc = umma_conv_check_coresident(pl);
-    float *skw = nullptr;
-    if (!rc && pl.p.splits > 1) {
-        const size_t nf = umma_conv_workspace_floats(pl) + umma_conv_ticket_words(pl);
-        if (cudaMalloc(&skw, nf * 4) != cudaSuccess || cudaMemsetAsync(skw, 0, nf * 4, s) != cudaSuccess) rc = B2_ERR_CUDA;
-        else umma_conv_set_workspace(&pl, skw, (unsigned int *)(skw + umma_conv_workspace_floats(pl)));
-    }
     if (!rc) {
         ConvParams &q = pl.p;
         q.stats = scratch;
@@ -341,12 +323,12 @@ int b2_conv_bn_test(int N, int Hi, int Wi, int Ci, int Co, int k, int stride, in
         q.fb_sync = (unsigned int *)(scratch + sums); q.fb_err = (int *)(scratch + sums + 4);
         q.fb_count = (float)g.M(); q.fb_inv_count = 1.0 / (double)g.M(); q.fb_eps = 1e-5f; q.fb_momentum = 0.1f; q.fb_relu = relu ? 1 : 0;
         if (timeline13) q.timeline = (long long *)(scratch + sums + 8);
-        if (info3) { info3[0] = pl.bn_tile; info3[1] = pl.grid; info3[2] = pl.p.total_tiles * 100 + pl.p.splits; }
+        if (info3) { info3[0] = pl.bn_tile; info3[1] = pl.grid; info3[2] = pl.p.total_tiles; }
         rc = umma_conv_launch(pl, s);
     }
     cudaError_t e = cudaStreamSynchronize(s);
     if (timeline13 && e == cudaSuccess) e = cudaMemcpy(timeline13, scratch + sums + 8, 13 * sizeof(long long), cudaMemcpyDeviceToHost);
-    cudaFree(w); cudaFree(scratch); cudaFree(skw);
+    cudaFree(w); cudaFree(scratch);
     if (rc == 0 && e != cudaSuccess) { set_error("conv_bn_test: %s", cudaGetErrorString(e)); rc = B2_ERR_CUDA; }
     return rc;
     GUARD_END

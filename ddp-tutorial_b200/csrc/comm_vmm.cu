@@ -91,6 +91,7 @@ static const char *drv_err(CUresult r) {
 
 struct VmmAlloc { CUdeviceptr ptr; size_t bytes; CUmemGenericAllocationHandle handle; bool owns_handle; };
 static std::vector<VmmAlloc> g_vmm;        // everything mapped by this process (own, imported, multicast)
+static size_t g_align = 0;                 // granularity reported by b2_vmm_query: every reservation is aligned to it
 
 static CUmemAllocationProp alloc_prop(int device) {
     CUmemAllocationProp prop{};
@@ -102,7 +103,7 @@ static CUmemAllocationProp alloc_prop(int device) {
 }
 static int map_handle(CUmemGenericAllocationHandle h, size_t bytes, size_t align, int device, bool owns, void **out) {
     CUdeviceptr va = 0;
-    B2_DRV(g_drv.MemAddressReserve(&va, bytes, align, 0, 0));
+    B2_DRV(g_drv.MemAddressReserve(&va, bytes, align ? align : g_align, 0, 0));
     B2_DRV(g_drv.MemMap(va, bytes, 0, h, 0));
     CUmemAccessDesc acc{};
     acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE; acc.location.id = device; acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
@@ -134,6 +135,7 @@ int b2_vmm_query(int device, int *multicast_supported, int64_t *granularity) {
         size_t mg = 0;
         if (g_drv.McGranularity(&mg, &mp, CU_MULTICAST_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && mg > g) g = mg;
     }
+    g_align = g;
     if (granularity) *granularity = (int64_t)g;
     return 0;
 }

@@ -27,15 +27,11 @@ struct ConvParams {
     int out_H, out_W, out_C, os;
     bf16 *out;
     int acc;                    // 1: out += result (bf16 read-modify-write)
+    int tma_store;              // 1: the staged bf16 tile goes to `out` with one TMA tile store per 64-channel half (dense lattice, no acc)
     int b_mn;                   // 0: B tile rows = output channel, cols = K (fprop)
                                 // 1: B tile rows = K (co), cols = output channel (dgrad reads the
                                 //    same [Co][taps*Ci] weight copy as an MN-major operand)
     int m_tiles, n_tiles, total_tiles;   // tile t = (class * n_tiles + n) * m_tiles + m
-    // split-K (few tiles, deep K): work item w = t * splits + split, CTA b runs w = b, b + grid, ...; each split adds its
-    // partial accumulators into the tile's fp32 workspace (red.global.add), the CTA drawing the last ticket finishes the tile
-    int splits;
-    float *ws;                  // [total_tiles][128][BN_TILE] fp32, all zero between launches (the finisher re-zeroes it)
-    unsigned int *tile_tickets; // [total_tiles], all zero between launches
     float *stats;               // optional [copies][2][out_C] per-channel sum / sum of squares (atomics); may be null
     // optional (dgrad that produces the FINAL gradient of a fused BatchNorm's output tensor): also
     // accumulate that BatchNorm's backward sums  sum(g), sum(g*xhat),  g = dY * [y > 0]
@@ -43,14 +39,6 @@ struct ConvParams {
     const bf16 *bn_x, *bn_y;    // the BatchNorm's input / output (same NHWC shape as `out`)
     const float *bn_mean, *bn_invstd;
     int bn_relu;
-    // optional on top of bn_bsum: finish that BatchNorm's backward in this kernel.  After the grid barrier
-    // every CTA turns its own tiles of g = dY*[y>0] into dz = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) (the
-    // gradient of the BatchNorm's INPUT) and the residual-branch gradient dres (+)= g: no separate apply kernel.
-    int bb_fuse;
-    bf16 *bb_dz, *bb_dres;      // dres may be null
-    int bb_acc_dz, bb_acc_dres;
-    const float *bb_gamma; float *bb_dgamma, *bb_dbeta;
-    float bb_inv_count;
     // optional (fprop): apply the consumer BatchNorm (+residual, ReLU) in this kernel.  After a CTA has
     // stored its tiles (bf16 conv output `out`, which backward needs anyway) and added their per-channel
     // sums to `stats`, it joins a grid-wide barrier (the grid is persistent: at most one CTA per SM, all
@@ -72,10 +60,11 @@ struct ConvParams {
 };
 
 struct UmmaConvPlan {
-    CUtensorMap a_map, b_map;
+    CUtensorMap a_map, b_map, out_map;
     ConvParams p;
     int bn_tile;                // 64 or 128 output channels per tile
     bool stem;                  // launch the gather variant (p.stem_x must be set before every launch)
+    bool shallow;               // 3-stage ring / 2 CTAs per SM variant (experiment: B2_CONV_SHALLOW=1)
     int grid;                   // persistent CTAs (<= SM count)
     double flops;               // executed FLOPs (dead taps skipped)
     bool valid;
@@ -89,6 +78,7 @@ struct WgradParams {
     int BW, BH, BN, h_blocks, a_hstep;
     int pix_tiles, tiles_per_split, splits;
     int m_boxes;                // Co tile = 64*m_boxes (1 or 2)
+    int cpt;                    // 64-wide K chunks per CTA: 3 when m_boxes == 1, else 2 (a stage holds 4 boxes)
     float *out;                 // dW (atomic / single-split mode) or compact partials [splits][Co][alive taps*Ci]
     int out_pitch;              // row pitch of `out` in floats
     int compact;                // 1: columns are (alive tap, ci); 0: columns are (tap id, ci) as in dW
@@ -114,10 +104,6 @@ int umma_plan_fprop(const ConvGeom &g, const bf16 *x, const bf16 *w, bf16 *y, Um
 // the 7x7 / stride 2 / pad 3 / 3-channel stem on 32x32 images as a 1x1 conv over virtual im2col rows of kpad = 192 columns
 bool umma_stem_supported(const ConvGeom &stem, const ConvGeom &virt, int kpad);
 int umma_plan_dgrad(const ConvGeom &g, const bf16 *dy, const bf16 *w, bf16 *dx, bool acc, UmmaConvPlan *plan);
-// split-K scratch a plan needs (0 when it does not split); one buffer pair can serve every plan of a stream
-size_t umma_conv_workspace_floats(const UmmaConvPlan &plan);
-size_t umma_conv_ticket_words(const UmmaConvPlan &plan);
-void umma_conv_set_workspace(UmmaConvPlan *plan, float *ws, unsigned int *tickets);
 // checks (once per plan) that the persistent grid is co-resident; required before enabling fuse_bn
 int umma_conv_check_coresident(const UmmaConvPlan &plan);
 int umma_conv_launch(const UmmaConvPlan &plan, cudaStream_t s);

@@ -278,10 +278,7 @@ int Model::finalize() {
     }
     size_t sums_off = reserve(sums_floats * 4 + 256);
     size_t err_off = reserve(256);
-    // split-K scratch: a splitting plan has tiles * splits <= #SMs, i.e. at most 74 tiles of 128 x 128 fp32
-    splitk_ws_floats = precision == B2_PREC_BF16 ? (size_t)(kNumSMs / 2) * 128 * 128 : 0;
-    splitk_ticket_words = precision == B2_PREC_BF16 ? 256 : 0;
-    size_t sk_off = reserve(splitk_ws_floats * 4 + 256), skt_off = reserve(splitk_ticket_words * 4 + 256);
+
     size_t wg_off = reserve(wg_floats * 4 + 256);
     size_t bf_off = precision == B2_PREC_BF16 ? reserve((size_t)n_params * 2 + 256) : 0;
     wgrad_floats = wg_floats;
@@ -306,7 +303,7 @@ int Model::finalize() {
     wgrad_ws = (float *)(base + wg_off);
     bn_sums = (float *)(base + sums_off); bn_sums_bytes = sums_floats * 4;
     fb_err = (int *)(base + err_off);
-    splitk_ws = (float *)(base + sk_off); splitk_tickets = (unsigned int *)(base + skt_off);
+
     for (size_t i = 0; i < ops.size(); ++i)
         if (ops[i].type == OP_BN && ops[i].bn_fused) {
             ops[i].fsum = bn_sums + sum_off[i]; ops[i].bsum = ops[i].fsum + 2 * (size_t)kBnSumCopies * tensors[ops[i].in].C;
@@ -466,7 +463,7 @@ int Model::build_plans() {
             B2_TRY(umma_plan_fprop(o.vg, o.col, o.wpad, (bf16 *)to.val, &o.fplan));
             // gather the im2col rows in shared memory straight from the fp32 image (no 50 MB im2col round trip)
             static const bool gather = [] { const char *e = getenv("B2_STEM_GATHER"); return !(e && e[0] == '0'); }();
-            o.stem_gather = gather && umma_stem_supported(o.g, o.vg, o.kpad) && o.fplan.bn_tile == 64 && o.fplan.p.splits == 1;
+            o.stem_gather = gather && umma_stem_supported(o.g, o.vg, o.kpad) && o.fplan.bn_tile == 64;
             o.fplan.stem = o.stem_gather;
             B2_TRY(umma_plan_wgrad(o.vg, o.col, (const bf16 *)to.grad, o.dwpad, wgrad_ws, wgrad_floats, deterministic, &o.wplan));
             if (o.wplan.p.atomic) zero_grads_each_step = true;
@@ -487,15 +484,6 @@ int Model::build_plans() {
         B2_TRY(umma_wgrad_zero_dead(o.wplan, 0));      // once: dead-tap gradients are exactly zero and never rewritten
     }
     B2_CUDA(cudaStreamSynchronize(0));
-    for (Op &o : ops) {
-        if (o.type != OP_CONV || !(o.use_umma || o.stem_umma)) continue;
-        for (UmmaConvPlan *pl : {&o.fplan, &o.dplan}) {
-            if (!pl->valid || pl->p.splits == 1) continue;
-            B2_CHECK(umma_conv_workspace_floats(*pl) <= splitk_ws_floats && umma_conv_ticket_words(*pl) <= splitk_ticket_words, B2_ERR_STATE,
-                     "split-K workspace too small (%zu floats needed)", umma_conv_workspace_floats(*pl));
-            umma_conv_set_workspace(pl, splitk_ws, splitk_tickets);
-        }
-    }
     for (Op &b : ops) {
         if (b.type != OP_BN || !b.bn_fused) continue;
         b.fwd_in_conv = false;
@@ -522,7 +510,7 @@ int Model::build_plans() {
                 }
             }
         // last writer of d(b.out) in backward order = its first consumer in forward order
-        b.bwd_sums_fused = false; b.bwd_apply_fused = false;
+        b.bwd_sums_fused = false;
         for (Op &c : ops) {
             bool consumes = (c.in == b.out) || (c.res == b.out);
             if (!consumes) continue;
@@ -535,18 +523,6 @@ int Model::build_plans() {
                 q.bn_bsum = b.bsum; q.bn_x = (const bf16 *)tensors[b.in].val; q.bn_y = (const bf16 *)tensors[b.out].val;
                 q.bn_mean = b.bn.mean; q.bn_invstd = b.bn.invstd; q.bn_relu = b.relu ? 1 : 0;
                 b.bwd_sums_fused = true;
-                // ... and the apply as well, behind the same kind of grid barrier the forward fusion uses
-                static const bool fuse_apply = [] { const char *e = getenv("B2_FUSE_BN_APPLY"); return !(e && e[0] == '0'); }();
-                if (fuse_apply && umma_conv_check_coresident(c.dplan) == 0) {
-                    const Tensor &tz = tensors[b.in];
-                    q.bb_fuse = 1;
-                    q.bb_dz = (bf16 *)tz.grad; q.bb_dres = b.res >= 0 ? (bf16 *)tensors[b.res].grad : nullptr;
-                    q.bb_acc_dz = b.acc_in ? 1 : 0; q.bb_acc_dres = b.acc_res ? 1 : 0;
-                    q.bb_gamma = p_params + b.w_off; q.bb_dgamma = p_grads + b.w_off; q.bb_dbeta = p_grads + b.b_off;
-                    q.bb_inv_count = 1.f / (float)((int64_t)tz.N * tz.H * tz.W);
-                    q.fb_sync = b.fb_counter + 2; q.fb_err = fb_err;
-                    b.bwd_apply_fused = true;
-                }
             }
             break;      // only the first consumer matters
         }
@@ -843,13 +819,12 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
             break;
         }
         case OP_BN: {
-            if (o.bn_fused && o.bwd_apply_fused) break;      // done inside the dgrad kernel that finalised d(o.out)
             int64_t M = (int64_t)ti.N * ti.H * ti.W;
             int ph = prof_begin(PC_BN_BWD, 0, ti.numel * (double)dt_size(ti.dt) * (o.res >= 0 ? 7.0 : 6.0), s);
             if (o.bn_fused)
                 B2_TRY(op_bn_backward_fused(ti.val, to.val, to.grad, ti.grad, o.res >= 0 ? tensors[o.res].grad : nullptr, ti.dt, M,
                                             ti.C, o.bsum, p_params + o.w_off, p_grads + o.w_off, p_grads + o.b_off, o.relu,
-                                            o.acc_in, o.acc_res, o.bwd_sums_fused || o.pool_sums_ready, o.bn, s));
+                                            o.acc_in, o.acc_res, o.bwd_sums_fused, o.bn, s));
             else
             B2_TRY(op_bn_backward(ti.val, to.val, to.grad, ti.grad, o.res >= 0 ? tensors[o.res].grad : nullptr, ti.dt, M,
                                   ti.C, p_params + o.w_off, p_grads + o.w_off, p_grads + o.b_off, o.relu, o.acc_in,
@@ -859,19 +834,6 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
         }
         case OP_MAXPOOL:
             if (o.need_dgrad) {
-                // the pool's input is the output of a fused BatchNorm (the stem): produce that BatchNorm's backward sums
-                // in the same pass -- the BN op that follows in this loop then only runs its apply kernel
-                Op *pb = nullptr;
-                for (Op &b : ops) if (b.type == OP_BN && b.out == o.in && b.bn_fused && !b.bwd_sums_fused) pb = &b;
-                static const bool fuse_pool = [] { const char *e = getenv("B2_FUSE_POOL_BN"); return !(e && e[0] == '0'); }();
-                bool sole = true;
-                for (const Op &c : ops) if (&c != &o && (c.in == o.in || c.res == o.in)) sole = false;      // pool is the only consumer
-                if (fuse_pool && pb && sole && ti.dt == DT_BF16 && !o.out_nchw && o.g.Ci % 8 == 0 && 256 % (o.g.Ci / 8) == 0) {
-                    B2_TRY(op_maxpool_backward_bn_reduce((const bf16 *)to.grad, o.idx, (bf16 *)ti.grad, (const bf16 *)ti.val,
-                                                         (const bf16 *)tensors[pb->in].val, pb->bn.mean, pb->bn.invstd, pb->bsum, o.g.N, o.g.Hi,
-                                                         o.g.Wi, o.g.Ci, o.g.kh, o.g.stride, o.g.pad, o.g.Ho, o.g.Wo, o.acc_in, pb->relu, s));
-                    pb->pool_sums_ready = true;
-                } else
                 if (ti.dt == DT_BF16 && !o.out_nchw && o.g.Ci % 8 == 0)
                     B2_TRY(op_maxpool_backward_bf16x8((const bf16 *)to.grad, o.idx, (bf16 *)ti.grad, o.g.N, o.g.Hi, o.g.Wi, o.g.Ci,
                                                       o.g.kh, o.g.stride, o.g.pad, o.g.Ho, o.g.Wo, o.acc_in, s));

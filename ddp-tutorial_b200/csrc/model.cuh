@@ -30,8 +30,6 @@ struct Op {
     bool fwd_in_conv;            // forward done inside the producing conv kernel (grid-barrier fusion)
     unsigned int *fb_counter;    // [0] arrivals, [1] generation of the fused conv+BN grid barrier
     bool bwd_sums_fused;         // the dgrad that finalises this BN's output gradient also accumulates bsum
-    bool pool_sums_ready;        // the max-pool backward that produced d(out) also accumulated bsum (stem)
-    bool bwd_apply_fused;        // ... and, after a grid barrier, applies this BN's backward itself (no kernel for this op)
     uint8_t *idx;                // maxpool argmax
     int wdt, wpitch;             // conv: weight operand type / row pitch as the kernels see it
     bool use_umma;               // tcgen05 path (bf16, channel counts multiples of 64)
@@ -70,8 +68,6 @@ struct Model {
     void *slab = nullptr; size_t slab_bytes = 0;
     float *wgrad_ws = nullptr; size_t wgrad_floats = 0;
     int *fb_err = nullptr;           // set by a fused conv+BN kernel whose grid barrier timed out
-    float *splitk_ws = nullptr; unsigned int *splitk_tickets = nullptr;   // shared by every split-K conv launch (one stream)
-    size_t splitk_ws_floats = 0, splitk_ticket_words = 0;
     float *bn_sums = nullptr; size_t bn_sums_bytes = 0;    // all fused-BN sum buffers, zeroed once per step
     bool weights_dirty = true;
     bool plans_ready = false;

@@ -58,11 +58,6 @@ int op_maxpool_forward_bf16x8(const bf16 *x, bf16 *y, uint8_t *idx, int N, int H
 int op_maxpool_backward_bf16x8(const bf16 *dy, const uint8_t *idx, bf16 *dx, int N, int Hi, int Wi, int C, int k,
                                int stride, int pad, int Ho, int Wo, bool acc, cudaStream_t s);
 
-// max-pool backward + the BatchNorm-backward sums of the BatchNorm whose output feeds the pool (stem), one pass
-int op_maxpool_backward_bn_reduce(const bf16 *dy, const uint8_t *idx, bf16 *dx, const bf16 *y, const bf16 *z, const float *mean,
-                                  const float *invstd, float *bsum, int N, int Hi, int Wi, int C, int k, int stride, int pad, int Ho, int Wo,
-                                  bool acc, bool relu, cudaStream_t s);
-
 // ---- stem: fp32 NCHW image -> bf16 im2col rows [N*Ho*Wo][kpad] for a k x k / stride / pad conv,
 // column order (kh, kw, c) = the O,H,W,I weight order; columns >= k*k*C are zero
 int op_stem_im2col(const float *x_nchw, bf16 *col, int N, int C, int H, int W, int k, int stride, int pad, int Ho,

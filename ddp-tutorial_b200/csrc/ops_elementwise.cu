@@ -523,10 +523,12 @@ static inline int grid_for2(int64_t n, int block, int max_blocks = kNumSMs * 16)
     return (int)b;
 }
 
+template <int KK, int SS, int PP>        // compile-time window / stride / pad (0 = use the runtime arguments)
 __global__ void __launch_bounds__(256)
 k_maxpool_fwd_bf16x8(const bf16 *__restrict__ x, bf16 *__restrict__ y, uint8_t *__restrict__ idx, int N, int Hi, int Wi,
-                     int C, int k, int stride, int pad, int Ho, int Wo) {
+                     int C, int k_, int stride_, int pad_, int Ho, int Wo) {
     pdl_sync();
+    const int k = KK ? KK : k_, stride = KK ? SS : stride_, pad = KK ? PP : pad_;
     const int C8 = C >> 3;
     const int64_t total = (int64_t)N * Ho * Wo * C8;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -562,14 +564,17 @@ int op_maxpool_forward_bf16x8(const bf16 *x, bf16 *y, uint8_t *idx, int N, int H
                               int pad, int Ho, int Wo, cudaStream_t s) {
     B2_CHECK(C % 8 == 0, B2_ERR_ARG, "maxpool x8: C must be a multiple of 8");
     int64_t total = (int64_t)N * Ho * Wo * (C / 8);
-    B2_LAUNCH(k_maxpool_fwd_bf16x8, grid_for2(total, 256), 256, 0, s, x, y, idx, N, Hi, Wi, C, k, stride, pad, Ho, Wo);
+    if (k == 3 && stride == 2 && pad == 1) { B2_LAUNCH((k_maxpool_fwd_bf16x8<3, 2, 1>), grid_for2(total, 256), 256, 0, s, x, y, idx, N, Hi, Wi, C, k, stride, pad, Ho, Wo); }
+    else { B2_LAUNCH((k_maxpool_fwd_bf16x8<0, 0, 0>), grid_for2(total, 256), 256, 0, s, x, y, idx, N, Hi, Wi, C, k, stride, pad, Ho, Wo); }
     return 0;
 }
 
+template <int KK, int SS, int PP>
 __global__ void __launch_bounds__(256)
 k_maxpool_bwd_bf16x8(const bf16 *__restrict__ dy, const uint8_t *__restrict__ idx, bf16 *__restrict__ dx, int N, int Hi,
-                     int Wi, int C, int k, int stride, int pad, int Ho, int Wo, bool acc) {
+                     int Wi, int C, int k_, int stride_, int pad_, int Ho, int Wo, bool acc) {
     pdl_sync();
+    const int k = KK ? KK : k_, stride = KK ? SS : stride_, pad = KK ? PP : pad_;
     const int C8 = C >> 3;
     const int64_t total = (int64_t)N * Hi * Wi * C8;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -609,7 +614,8 @@ int op_maxpool_backward_bf16x8(const bf16 *dy, const uint8_t *idx, bf16 *dx, int
                                int stride, int pad, int Ho, int Wo, bool acc, cudaStream_t s) {
     B2_CHECK(C % 8 == 0, B2_ERR_ARG, "maxpool x8: C must be a multiple of 8");
     int64_t total = (int64_t)N * Hi * Wi * (C / 8);
-    B2_LAUNCH(k_maxpool_bwd_bf16x8, grid_for2(total, 256), 256, 0, s, dy, idx, dx, N, Hi, Wi, C, k, stride, pad, Ho, Wo, acc);
+    if (k == 3 && stride == 2 && pad == 1) { B2_LAUNCH((k_maxpool_bwd_bf16x8<3, 2, 1>), grid_for2(total, 256), 256, 0, s, dy, idx, dx, N, Hi, Wi, C, k, stride, pad, Ho, Wo, acc); }
+    else { B2_LAUNCH((k_maxpool_bwd_bf16x8<0, 0, 0>), grid_for2(total, 256), 256, 0, s, dy, idx, dx, N, Hi, Wi, C, k, stride, pad, Ho, Wo, acc); }
     return 0;
 }
 
@@ -786,7 +792,18 @@ __global__ void __launch_bounds__(256)
 k_head_fwd(const T *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias, float *__restrict__ feat,
            float *__restrict__ y, int B, int HW, int C, int N) {
     pdl_sync();
-    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    // The weight rows are C*4 bytes apart (2 KB for ResNet-18): read straight from global, the N rows of one channel
+    // block collide in the L1 sets and every access goes to L2 (measured 28-47 us for this 5 MFLOP layer).  So the
+    // block first copies W [N][C] into shared memory with coalesced 16-byte loads; then one warp per image, lanes over
+    // channels (conflict-free shared reads), N accumulators per lane, butterfly at the end.
+    extern __shared__ float sw[];                       // [N][C]
+    {
+        const int n4 = N * C / 4;
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) ((float4 *)sw)[i] = __ldg((const float4 *)w + i);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= B) return;
     float acc[NMAX];
 #pragma unroll
@@ -798,20 +815,26 @@ k_head_fwd(const T *__restrict__ x, const float *__restrict__ w, const float *__
         feat[(int64_t)b * C + c] = s;
 #pragma unroll
         for (int n = 0; n < NMAX; ++n)
-            if (n < N) acc[n] = fmaf(s, __ldg(w + (int64_t)n * C + c), acc[n]);
+            if (n < N) acc[n] = fmaf(s, sw[n * C + c], acc[n]);
     }
 #pragma unroll
     for (int n = 0; n < NMAX; ++n) {
         if (n < N) {
-            float s = warp_sum(acc[n]);
+            const float s = warp_sum(acc[n]);
             if (lane == 0) y[(int64_t)b * N + n] = bias ? s + bias[n] : s;
         }
     }
 }
 int op_head_forward(const void *x, int xdt, const float *w, const float *bias, float *feat, float *y, int B, int HW, int C, int N,
                     cudaStream_t s) {
-    B2_CHECK(N <= 16, B2_ERR_UNSUPPORTED, "fc head: at most 16 outputs");
-    DISPATCH_DT(xdt, T, B2_LAUNCH((k_head_fwd<T, 16>), (int)ceil_div((int64_t)B * 32, 256), 256, 0, s, (const T *)x, w, bias, feat, y, B, HW, C, N));
+    B2_CHECK(N <= 16 && (N * C) % 4 == 0 && (size_t)N * C * 4 <= 160 * 1024, B2_ERR_UNSUPPORTED, "fc head: %d x %d weights do not fit the shared-memory copy", N, C);
+    static const bool attr_set = [] {
+        cudaFuncSetAttribute(k_head_fwd<float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_head_fwd<bf16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        return true;
+    }();
+    (void)attr_set;
+    DISPATCH_DT(xdt, T, B2_LAUNCH((k_head_fwd<T, 16>), (int)ceil_div(B, 8), 256, (size_t)N * C * sizeof(float), s, (const T *)x, w, bias, feat, y, B, HW, C, N));
     return 0;
 }
 template <typename T>
@@ -1104,93 +1127,6 @@ int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx,
     B2_LAUNCH((k_bn_bwd_apply_fused<bf16, 8>), (int)blocks, 256, 3 * C * sizeof(float), s, (const bf16 *)x, (const bf16 *)y,
               (const bf16 *)dy, (bf16 *)dx, (bf16 *)dres, w.mean, w.invstd, bsum, gamma, dgamma, dbeta, M, relu, acc_dx, acc_dres,
               total, C);
-    return 0;
-}
-
-// Max-pool backward fused with the BatchNorm-backward reduction of the BatchNorm that feeds the pool (the stem:
-// conv1 -> bn1 -> relu -> maxpool, torchvision resnet.py:268-271).  dx = d(pool input) is written (it is the dy of bn1),
-// and in the same pass the sums  sum(g), sum(g * xhat),  g = dx * [y > 0]  go to bsum[copies][2][C]: one pass over
-// (y, z) instead of a max-pool backward kernel followed by a reduce kernel that re-reads its output.
-__global__ void __launch_bounds__(256)
-k_maxpool_bwd_bn_reduce(const bf16 *__restrict__ dy, const uint8_t *__restrict__ idx, bf16 *__restrict__ dx, const bf16 *__restrict__ y,
-                        const bf16 *__restrict__ z, const float *__restrict__ mean, const float *__restrict__ invstd, float *__restrict__ bsum,
-                        int N, int Hi, int Wi, int C, int k, int stride, int pad, int Ho, int Wo, bool acc, bool relu) {
-    pdl_sync();
-    const int C8 = C >> 3;                       // host guarantees (gridDim.x * 256) % C8 == 0 and 256 % C8 == 0
-    const int c8 = threadIdx.x % C8;
-    const int64_t total = (int64_t)N * Hi * Wi * C8;
-    float s0[8], s1[8], mu[8], is[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { s0[e] = 0.f; s1[e] = 0.f; mu[e] = mean[c8 * 8 + e]; is[e] = invstd[c8 * 8 + e]; }
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = i / C8;
-        int wi = r % Wi; r /= Wi;
-        int hi = r % Hi; int n = r / Hi;
-        float g[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) g[e] = 0.f;
-        int oh_lo = hi + pad - k + stride; oh_lo = oh_lo < 0 ? 0 : oh_lo / stride;
-        int oh_hi = (hi + pad) / stride; if (oh_hi > Ho - 1) oh_hi = Ho - 1;
-        int ow_lo = wi + pad - k + stride; ow_lo = ow_lo < 0 ? 0 : ow_lo / stride;
-        int ow_hi = (wi + pad) / stride; if (ow_hi > Wo - 1) ow_hi = Wo - 1;
-        for (int oh = oh_lo; oh <= oh_hi; ++oh)
-            for (int ow = ow_lo; ow <= ow_hi; ++ow) {
-                const int mine = (hi - (oh * stride - pad)) * k + (wi - (ow * stride - pad));
-                const int64_t o = ((((int64_t)n * Ho + oh) * Wo + ow) * C8 + c8) * 8;
-                uint2 iraw = *(const uint2 *)(idx + o);
-                uint4 draw = *(const uint4 *)(dy + o);
-                const uint8_t *ix = (const uint8_t *)&iraw; const bf16 *dv = (const bf16 *)&draw;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) if (ix[e] == mine) g[e] += __bfloat162float(dv[e]);
-            }
-        if (acc) {
-            uint4 old = *(const uint4 *)(dx + i * 8);
-            const bf16 *ov = (const bf16 *)&old;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) g[e] += __bfloat162float(ov[e]);
-        }
-        __align__(16) bf16 o8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o8[e] = __float2bfloat16_rn(g[e]);
-        *(uint4 *)(dx + i * 8) = *(uint4 *)o8;
-        const uint4 yr = *(const uint4 *)(y + i * 8), zr = *(const uint4 *)(z + i * 8);
-        const bf16 *yv = (const bf16 *)&yr, *zv = (const bf16 *)&zr;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float ge = __bfloat162float(o8[e]);                       // the stored (bf16) gradient, as the apply kernel reads it
-            if (relu && !(__bfloat162float(yv[e]) > 0.f)) ge = 0.f;
-            s0[e] += ge; s1[e] = fmaf(ge, (__bfloat162float(zv[e]) - mu[e]) * is[e], s1[e]);
-        }
-    }
-    // threads with equal (threadIdx % C8) own the same channels
-    __shared__ float sh[256 * 17];
-    float *mine_ = sh + threadIdx.x * 17;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { mine_[e] = s0[e]; mine_[8 + e] = s1[e]; }
-    __syncthreads();
-    const int lanes = 256 / C8, ty = threadIdx.x / C8;
-    for (int st = lanes >> 1; st > 0; st >>= 1) {
-        if (ty < st) {
-            const float *other = sh + (threadIdx.x + st * C8) * 17;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) mine_[e] += other[e];
-        }
-        __syncthreads();
-    }
-    if (ty == 0) {
-        float *dst = bsum + (size_t)(blockIdx.x % kBnSumCopies) * 2 * C;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { atomicAdd(dst + c8 * 8 + e, mine_[e]); atomicAdd(dst + C + c8 * 8 + e, mine_[8 + e]); }
-    }
-}
-int op_maxpool_backward_bn_reduce(const bf16 *dy, const uint8_t *idx, bf16 *dx, const bf16 *y, const bf16 *z, const float *mean,
-                                  const float *invstd, float *bsum, int N, int Hi, int Wi, int C, int k, int stride, int pad, int Ho, int Wo,
-                                  bool acc, bool relu, cudaStream_t s) {
-    const int C8 = C / 8;
-    B2_CHECK(C % 8 == 0 && C8 <= 256 && 256 % C8 == 0 && ((256 / C8) & (256 / C8 - 1)) == 0, B2_ERR_ARG, "maxpool+bn reduce: unsupported channel count %d", C);
-    int64_t total = (int64_t)N * Hi * Wi * C8;
-    int blocks = (int)ceil_div(total, 256 * 4); if (blocks > kNumSMs * 4) blocks = kNumSMs * 4; if (blocks < 1) blocks = 1;
-    B2_LAUNCH(k_maxpool_bwd_bn_reduce, blocks, 256, 0, s, dy, idx, dx, y, z, mean, invstd, bsum, N, Hi, Wi, C, k, stride, pad, Ho, Wo, acc, relu);
     return 0;
 }
 

@@ -62,6 +62,7 @@ for n, t in r["final"]:
     perr = max(perr, float((a - t).abs().max() / (t.abs().max() + 1e-12)))
 print(f"rank {rank} max param rel err {perr:.3e}")
 ok &= perr < (1e-4 if name == "net" else (5e-2 if prec == "fp32" else 1.0))   # ResNet: chaotic growth of rounding noise
+print(f"rank {rank} NVLS (multimem all-reduce) active: {bool(b2.lib().b2_comm_nvls_active())}")
 print(f"rank {rank} buckets: {b2.lib().b2_model_num_buckets(net.module.engine._model(B).h)}")
 # replicas bit-identical
 import torch.distributed as dist
