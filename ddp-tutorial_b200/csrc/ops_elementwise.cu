@@ -808,14 +808,34 @@ k_head_fwd(const T *__restrict__ x, const float *__restrict__ w, const float *__
     float acc[NMAX];
 #pragma unroll
     for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
-    for (int c = lane; c < C; c += 32) {
-        float s = 0.f;
-        for (int p = 0; p < HW; ++p) s += to_f<T>(x[((int64_t)b * HW + p) * C + c]);
-        s = s / (float)HW;
-        feat[(int64_t)b * C + c] = s;
+    if (HW == 1) {
+        // 1x1 feature map (32x32 inputs): 16 independent activation loads in flight per lane, then the multiply-adds
+        const T *xr = x + (int64_t)b * C;
+        for (int c0 = lane; c0 < C; c0 += 512) {
+            float xv[16];
 #pragma unroll
-        for (int n = 0; n < NMAX; ++n)
-            if (n < N) acc[n] = fmaf(s, sw[n * C + c], acc[n]);
+            for (int j = 0; j < 16; ++j) { const int c = c0 + 32 * j; xv[j] = c < C ? to_f<T>(xr[c]) : 0.f; }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int c = c0 + 32 * j;
+                if (c < C) {
+                    feat[(int64_t)b * C + c] = xv[j];
+#pragma unroll
+                    for (int n = 0; n < NMAX; ++n)
+                        if (n < N) acc[n] = fmaf(xv[j], sw[n * C + c], acc[n]);
+                }
+            }
+        }
+    } else {
+        for (int c = lane; c < C; c += 32) {
+            float s = 0.f;
+            for (int p = 0; p < HW; ++p) s += to_f<T>(x[((int64_t)b * HW + p) * C + c]);
+            s = s / (float)HW;
+            feat[(int64_t)b * C + c] = s;
+#pragma unroll
+            for (int n = 0; n < NMAX; ++n)
+                if (n < N) acc[n] = fmaf(s, sw[n * C + c], acc[n]);
+        }
     }
 #pragma unroll
     for (int n = 0; n < NMAX; ++n) {

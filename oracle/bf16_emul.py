@@ -142,10 +142,10 @@ def local_backward(model: torch.nn.Module, x: torch.Tensor, ours: List[Tuple[tor
     def leaf(k):
         return ours[k][0].detach().clone().requires_grad_(True)
 
-    def vjp(out, ins, params):
+    def vjp(out, ins, params, out_fwd=None):
         """ins: [(leaf tensor, producer op index)], params: [parameter names]; upstream = our grad of this op."""
         k = idx[0]
-        fwd.append(out.detach())
+        fwd.append((out if out_fwd is None else out_fwd).detach())
         up = ours[k][1].reshape(out.shape)
         ts = [t for t, _ in ins] + [names[n] for n in params]
         gs = torch.autograd.grad(out, ts, grad_outputs=up, allow_unused=True)
@@ -170,9 +170,12 @@ def local_backward(model: torch.nn.Module, x: torch.Tensor, ours: List[Tuple[tor
             r_ = leaf(res_src)
             ins.append((r_, res_src))
             y = y + r_
+        out_fwd = F.relu(y) if relu else y
         if relu:
-            y = F.relu(y)
-        return vjp(y, ins, [pname + ".weight", pname + ".bias"])
+            # backward through the ReLU with the mask of the STORED output (what the CUDA path tests, y > 0): a
+            # pre-activation within one bf16 ulp of zero may round to the other side when recomputed here
+            y = y * (ours[idx[0]][0].reshape(y.shape) > 0).to(y.dtype)
+        return vjp(y, ins, [pname + ".weight", pname + ".bias"], out_fwd)
 
     k = conv("conv1", model.conv1, None, x.bfloat16().float())
     k = bn("bn1", model.bn1, k, True)
