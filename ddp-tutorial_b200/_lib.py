@@ -24,6 +24,8 @@ _SIGS = {
     "b2_version": (_i, []),
     "b2_last_error": (C.c_char_p, []),
     "b2_launch_count": (_i64, []),
+    "b2_trace_start": (_i, [_i]),
+    "b2_trace_stop": (_i, [_vp, _i, C.POINTER(_i)]),
     "b2_model_create": (_i, [_i, _i, _i, _i, _i, C.POINTER(_vp)]),
     "b2_model_destroy": (_i, [_vp]),
     "b2_model_param_count": (_i64, [_vp]),

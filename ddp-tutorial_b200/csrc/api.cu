@@ -37,6 +37,44 @@ int b2_version(void) { return 100; }
 const char *b2_last_error(void) { return g_err; }
 int64_t b2_launch_count(void) { return g_launches; }
 
+/* ---- in-graph kernel trace (common.cuh: trace_mark) ---- */
+static unsigned long long *g_trace_buf = nullptr;
+static unsigned int *g_trace_cnt = nullptr;
+static unsigned int g_trace_cap = 0;
+static int trace_install_all(unsigned long long *buf, unsigned int *cnt, unsigned int cap) {
+    B2_TRY(trace_install_comm(buf, cnt, cap));
+    B2_TRY(trace_install_simt(buf, cnt, cap));
+    B2_TRY(trace_install_umma(buf, cnt, cap));
+    B2_TRY(trace_install_elem(buf, cnt, cap));
+    return 0;
+}
+int b2_trace_start(int capacity) {
+    B2_CHECK(capacity > 0 && capacity <= (1 << 20), B2_ERR_ARG, "trace_start: capacity out of range");
+    B2_CUDA(cudaDeviceSynchronize());
+    if (g_trace_buf) { trace_install_all(nullptr, g_trace_cnt, 0); cudaFree(g_trace_buf); cudaFree(g_trace_cnt); g_trace_buf = nullptr; }
+    B2_CUDA(cudaMalloc(&g_trace_buf, (size_t)capacity * 16));
+    B2_CUDA(cudaMalloc(&g_trace_cnt, sizeof(unsigned int)));
+    B2_CUDA(cudaMemset(g_trace_cnt, 0, sizeof(unsigned int)));
+    g_trace_cap = (unsigned int)capacity;
+    int r = trace_install_all(g_trace_buf, g_trace_cnt, g_trace_cap);
+    if (r) set_error("trace_start: cudaMemcpyToSymbol failed");
+    return r;
+}
+int b2_trace_stop(unsigned long long *records, int max_records, int *n_out) {
+    B2_CHECK(g_trace_buf && records && n_out, B2_ERR_STATE, "trace_stop: no trace running / NULL argument");
+    B2_CUDA(cudaDeviceSynchronize());
+    unsigned int n = 0;
+    B2_CUDA(cudaMemcpy(&n, g_trace_cnt, sizeof(n), cudaMemcpyDeviceToHost));
+    if (n > g_trace_cap) n = g_trace_cap;
+    if ((int)n > max_records) n = (unsigned int)max_records;
+    B2_CUDA(cudaMemcpy(records, g_trace_buf, (size_t)n * 16, cudaMemcpyDeviceToHost));
+    *n_out = (int)n;
+    trace_install_all(nullptr, g_trace_cnt, 0);
+    cudaFree(g_trace_buf); cudaFree(g_trace_cnt);
+    g_trace_buf = nullptr; g_trace_cnt = nullptr; g_trace_cap = 0;
+    return 0;
+}
+
 int b2_model_create(int kind, int batch, int num_classes, int precision, int device, b2_model **out) {
     GUARD_BEGIN
     B2_CHECK(out, B2_ERR_ARG, "b2_model_create: out is NULL");
@@ -205,6 +243,9 @@ int b2_model_read_activation(b2_model *h, int op, int want_grad, float *out, int
     if (shape) { shape[0] = t.N; shape[1] = t.C; shape[2] = t.H; shape[3] = t.W; }
     if (!out) return 0;
     B2_CHECK(capacity >= t.numel, B2_ERR_ARG, "read_activation: capacity %lld < %lld", (long long)capacity, (long long)t.numel);
+    B2_CHECK(!(want_grad && o.type == OP_BN && o.bn_fused && o.pool_op >= 0), B2_ERR_UNSUPPORTED,
+             "read_activation: the gradient of op %d's output is never materialised (the max pooling's backward is recomputed "
+             "inside this BatchNorm's backward kernels; B2_FUSE_POOL_BWD=0 keeps the tensor)", op);
     const void *src = want_grad ? t.grad : t.val;
     if (o.type == OP_MAXPOOL && o.out_nchw) {   // already NCHW-flat
         B2_CHECK(t.dt == DT_F32, B2_ERR_UNSUPPORTED, "read_activation: flat bf16 tensor");

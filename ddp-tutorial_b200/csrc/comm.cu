@@ -14,18 +14,37 @@
 //              slice into all W replicas (all-gather of params, not grads)
 // so neither a separate all-reduce nor a separate elementwise optimizer kernel exists.
 // Summation order is fixed (rank 0..W-1) => replicas stay bit-identical.
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
+#define B2_TRACE_TU_ID 1
 #include "ops.cuh"
 
 namespace b2 {
 
 constexpr int kMaxWorld = 8;
-constexpr int kCommBlocks = 96;       // blocks per comm kernel (all co-resident; same on every rank)
-constexpr int kCommThreads = 512;
+constexpr int kCommBlocks = 148;      // most blocks a comm kernel launches (flag slots; same on every rank)
+constexpr int kCommThreadsMax = 512;
+// Launch shape of the exchange kernels (B2_COMM_THREADS / B2_COMM_BLOCKS override; same value on every rank).
+// Measured at W=2 on ResNet-18 (profiles/r02_comm_shape_sweep.txt): 96 x 512 beats 148 x 128 and 96/148 x 256 although
+// only the small CTAs fit beside a persistent conv CTA (352 threads x 120 registers): the exchange slows the step mostly
+// through the memory system (latency-bound kernels next to it run 2-3x longer, tools/step_trace.py), so the shortest
+// exchange wins, not the most polite one.
+static int comm_threads() {
+    static const int v = [] { const char *e = getenv("B2_COMM_THREADS"); int t = e ? atoi(e) : 0;
+                              return (t >= 32 && t <= kCommThreadsMax && t % 32 == 0) ? t : 512; }();
+    return v;
+}
+static int comm_blocks() {
+    static const int v = [] { const char *e = getenv("B2_COMM_BLOCKS"); int t = e ? atoi(e) : 0;
+                              return (t > 0 && t <= kCommBlocks) ? t : 96; }();
+    return v;
+}
 // flag layout (uint32 words): [phase 0/1][src rank][block]
 constexpr int kFlagStride = kCommBlocks;
+constexpr int kOneShotPerThread = 4;  // plain one-shot all-reduce keeps its sums in registers across the barrier
+constexpr int kMcBatch = 4;           // multimem.ld_reduce in flight per thread
 
 struct CommPtrs {
     float *grads[kMaxWorld];
@@ -78,11 +97,13 @@ __device__ __forceinline__ void peer_barrier(const CommPtrs &P, int rank, uint32
         epoch_mem[phase * kCommBlocks + blockIdx.x] = e;
         s_epoch = e;
     }
-    if (FENCE) __threadfence_system();      // publish this thread's earlier stores (incl. to peers)
-    __syncthreads();
+    __syncthreads();                        // every thread's earlier (peer) stores are ordered before the signalling threads' release
     const uint32_t e = s_epoch;
     if (threadIdx.x < W) {
         const int peer = threadIdx.x;
+        // one cumulative system-scope fence per signalling thread publishes the whole CTA's stores (bar.sync above
+        // orders them before it) -- a fence in all 512 threads costs several microseconds per barrier
+        if (FENCE) __threadfence_system();
         uint32_t *remote = P.flags[peer] + ((phase * kMaxWorld + rank) * kFlagStride + blockIdx.x);
         st_release_sys(remote, e);
         const uint32_t *mine = P.flags[rank] + ((phase * kMaxWorld + peer) * kFlagStride + blockIdx.x);
@@ -117,10 +138,10 @@ __device__ __forceinline__ void sgd_apply(float4 &p, float4 &m, const float4 g, 
 // MODE 0: plain all-reduce (result * scale written to every rank's grad buffer)
 // MODE 1: fused all-reduce/W + SGD-momentum (params updated on every rank)
 template <int W, int MODE, bool ONESHOT>
-__global__ void __launch_bounds__(kCommThreads)
+__global__ void __launch_bounds__(kCommThreadsMax)
 k_allreduce(const CommPtrs P, int rank, float *__restrict__ mom_buf, int64_t off, int64_t n4 /* float4 count */,
             float scale, float lr, float momentum, int first, bf16 *__restrict__ mirror, uint32_t *epoch_mem, int *err) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     peer_barrier<W, false>(P, rank, epoch_mem, 0, err);      // earlier kernels' stores are already visible
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,42 +161,62 @@ k_allreduce(const CommPtrs P, int rank, float *__restrict__ mom_buf, int64_t off
             }
             peer_barrier<W, false>(P, rank, epoch_mem, 1, err);      // peers are done reading my grads
         } else {
-            // at most one float4 per thread (host guarantees n4 <= grid*block): read all, barrier, write own
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int64_t e = off + tid * 4;
-            if (tid < n4) {
-                acc = ld_peer_f4(P.grads[0] + e);
+            // at most kOneShotPerThread float4 per thread (host guarantees n4 <= that * grid * block): read all, barrier, write own
+            float4 acc[kOneShotPerThread];
 #pragma unroll
-                for (int r = 1; r < W; ++r) acc = f4_add(acc, ld_peer_f4(P.grads[r] + e));
-                acc = f4_scale(acc, scale);
+            for (int u = 0; u < kOneShotPerThread; ++u) {
+                const int64_t i = tid + u * stride;
+                acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < n4) {
+                    const int64_t e = off + i * 4;
+                    acc[u] = ld_peer_f4(P.grads[0] + e);
+#pragma unroll
+                    for (int r = 1; r < W; ++r) acc[u] = f4_add(acc[u], ld_peer_f4(P.grads[r] + e));
+                    acc[u] = f4_scale(acc[u], scale);
+                }
             }
             peer_barrier<W, false>(P, rank, epoch_mem, 1, err);
-            if (tid < n4) *(float4 *)(P.grads[rank] + e) = acc;
+#pragma unroll
+            for (int u = 0; u < kOneShotPerThread; ++u) {
+                const int64_t i = tid + u * stride;
+                if (i < n4) *(float4 *)(P.grads[rank] + off + i * 4) = acc[u];
+            }
         }
     } else {
         // slice owned by this rank, in float4 units
         const int64_t per = (n4 + W - 1) / W;
         const int64_t lo = (int64_t)rank * per;
         int64_t hi = lo + per; if (hi > n4) hi = n4;
-#pragma unroll 2
-        for (int64_t i = lo + tid; i < hi; i += stride) {
-            const int64_t e = off + i * 4;
-            float4 part[W];
+        constexpr int U = W >= 8 ? 1 : (W == 4 ? 2 : 4);       // U * W peer loads in flight per thread (the asm loads are volatile: batch them by hand)
+        for (int64_t i0 = lo + tid; i0 < hi; i0 += stride * U) {
+            float4 part[U][W];
 #pragma unroll
-            for (int r = 0; r < W; ++r) part[r] = ld_peer_f4(P.grads[r] + e);     // all W loads in flight
-            float4 acc = part[0];
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + u * stride;
+                if (i < hi) {
 #pragma unroll
-            for (int r = 1; r < W; ++r) acc = f4_add(acc, part[r]);
-            acc = f4_scale(acc, scale);
-            if (MODE == 1) {
-                float4 p = *(float4 *)(P.params[rank] + e), m = first ? acc : *(float4 *)(mom_buf + e);
-                sgd_apply(p, m, acc, lr, momentum, first);
-                *(float4 *)(mom_buf + e) = m;
+                    for (int r = 0; r < W; ++r) part[u][r] = ld_peer_f4(P.grads[r] + off + i * 4);
+                }
+            }
 #pragma unroll
-                for (int r = 0; r < W; ++r) st_peer_f4(P.params[r] + e, p);
-            } else {
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + u * stride;
+                if (i >= hi) break;
+                const int64_t e = off + i * 4;
+                float4 acc = part[u][0];
 #pragma unroll
-                for (int r = 0; r < W; ++r) st_peer_f4(P.grads[r] + e, acc);
+                for (int r = 1; r < W; ++r) acc = f4_add(acc, part[u][r]);
+                acc = f4_scale(acc, scale);
+                if (MODE == 1) {
+                    float4 p = *(float4 *)(P.params[rank] + e), m = first ? acc : *(float4 *)(mom_buf + e);
+                    sgd_apply(p, m, acc, lr, momentum, first);
+                    *(float4 *)(mom_buf + e) = m;
+#pragma unroll
+                    for (int r = 0; r < W; ++r) st_peer_f4(P.params[r] + e, p);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < W; ++r) st_peer_f4(P.grads[r] + e, acc);
+                }
             }
         }
         peer_barrier<W>(P, rank, epoch_mem, 1, err);          // all slices have landed everywhere
@@ -187,6 +228,8 @@ k_allreduce(const CommPtrs P, int rank, float *__restrict__ mom_buf, int64_t off
             }
         }
     }
+    __syncthreads();
+    B2_TRACE_END();
 }
 
 
@@ -205,49 +248,78 @@ __device__ __forceinline__ void mc_st_f4(float *mc, float4 v) {
 // replicas and adds them in fp32) and the result / updated parameters go out with ONE multimem.st (the switch
 // writes all W replicas): each GPU moves 1/W of the bytes over its own links instead of (W-1)/W.
 template <int W, int MODE, bool ONESHOT>
-__global__ void __launch_bounds__(kCommThreads)
+__global__ void __launch_bounds__(kCommThreadsMax)
 k_allreduce_nvls(const CommPtrs P, int rank, float *__restrict__ mc_grads, float *__restrict__ mc_params, float *__restrict__ mom_buf,
                  int64_t off, int64_t n4, float scale, float lr, float momentum, int first, bf16 *__restrict__ mirror,
                  uint32_t *epoch_mem, int *err) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     peer_barrier<W, false>(P, rank, epoch_mem, 0, err);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ONESHOT) {
         // small buckets: every rank asks the switch for the whole sum and updates its own replica
         if (MODE == 1) {
-            for (int64_t i = tid; i < n4; i += stride) {
-                const int64_t e = off + i * 4;
-                float4 acc = f4_scale(mc_ld_reduce_f4(mc_grads + e), scale);
-                float4 p = *(float4 *)(P.params[rank] + e), m = first ? acc : *(float4 *)(mom_buf + e);
-                sgd_apply(p, m, acc, lr, momentum, first);
-                *(float4 *)(mom_buf + e) = m;
-                *(float4 *)(P.params[rank] + e) = p;
-                if (mirror) st_bf16x4(mirror + e, p);
+            for (int64_t i0 = tid; i0 < n4; i0 += stride * kMcBatch) {
+                float4 red[kMcBatch];
+#pragma unroll
+                for (int u = 0; u < kMcBatch; ++u) {
+                    const int64_t i = i0 + u * stride;
+                    if (i < n4) red[u] = mc_ld_reduce_f4(mc_grads + off + i * 4);
+                }
+#pragma unroll
+                for (int u = 0; u < kMcBatch; ++u) {
+                    const int64_t i = i0 + u * stride;
+                    if (i >= n4) break;
+                    const int64_t e = off + i * 4;
+                    float4 acc = f4_scale(red[u], scale);
+                    float4 p = *(float4 *)(P.params[rank] + e), m = first ? acc : *(float4 *)(mom_buf + e);
+                    sgd_apply(p, m, acc, lr, momentum, first);
+                    *(float4 *)(mom_buf + e) = m;
+                    *(float4 *)(P.params[rank] + e) = p;
+                    if (mirror) st_bf16x4(mirror + e, p);
+                }
             }
             peer_barrier<W, false>(P, rank, epoch_mem, 1, err);      // peers are done reading my grads
         } else {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int64_t e = off + tid * 4;
-            if (tid < n4) acc = f4_scale(mc_ld_reduce_f4(mc_grads + e), scale);
+            float4 acc[kOneShotPerThread];
+#pragma unroll
+            for (int u = 0; u < kOneShotPerThread; ++u) {
+                const int64_t i = tid + u * stride;
+                acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < n4) acc[u] = f4_scale(mc_ld_reduce_f4(mc_grads + off + i * 4), scale);
+            }
             peer_barrier<W, false>(P, rank, epoch_mem, 1, err);
-            if (tid < n4) *(float4 *)(P.grads[rank] + e) = acc;
+#pragma unroll
+            for (int u = 0; u < kOneShotPerThread; ++u) {
+                const int64_t i = tid + u * stride;
+                if (i < n4) *(float4 *)(P.grads[rank] + off + i * 4) = acc[u];
+            }
         }
     } else {
         const int64_t per = (n4 + W - 1) / W;
         const int64_t lo = (int64_t)rank * per;
         int64_t hi = lo + per; if (hi > n4) hi = n4;
-#pragma unroll 4
-        for (int64_t i = lo + tid; i < hi; i += stride) {
-            const int64_t e = off + i * 4;
-            float4 acc = f4_scale(mc_ld_reduce_f4(mc_grads + e), scale);
-            if (MODE == 1) {
-                float4 p = *(float4 *)(P.params[rank] + e), m = first ? acc : *(float4 *)(mom_buf + e);
-                sgd_apply(p, m, acc, lr, momentum, first);
-                *(float4 *)(mom_buf + e) = m;
-                mc_st_f4(mc_params + e, p);                     // all W replicas, mine included
-            } else {
-                mc_st_f4(mc_grads + e, acc);
+        for (int64_t i0 = lo + tid; i0 < hi; i0 += stride * kMcBatch) {
+            float4 red[kMcBatch];                               // kMcBatch switch reductions in flight per thread
+#pragma unroll
+            for (int u = 0; u < kMcBatch; ++u) {
+                const int64_t i = i0 + u * stride;
+                if (i < hi) red[u] = mc_ld_reduce_f4(mc_grads + off + i * 4);
+            }
+#pragma unroll
+            for (int u = 0; u < kMcBatch; ++u) {
+                const int64_t i = i0 + u * stride;
+                if (i >= hi) break;
+                const int64_t e = off + i * 4;
+                float4 acc = f4_scale(red[u], scale);
+                if (MODE == 1) {
+                    float4 p = *(float4 *)(P.params[rank] + e), m = first ? acc : *(float4 *)(mom_buf + e);
+                    sgd_apply(p, m, acc, lr, momentum, first);
+                    *(float4 *)(mom_buf + e) = m;
+                    mc_st_f4(mc_params + e, p);                     // all W replicas, mine included
+                } else {
+                    mc_st_f4(mc_grads + e, acc);
+                }
             }
         }
         peer_barrier<W>(P, rank, epoch_mem, 1, err);          // all slices have landed everywhere
@@ -258,12 +330,14 @@ k_allreduce_nvls(const CommPtrs P, int rank, float *__restrict__ mc_grads, float
             }
         }
     }
+    __syncthreads();
+    B2_TRACE_END();
 }
 
 template <int W>
-__global__ void __launch_bounds__(kCommThreads)
+__global__ void __launch_bounds__(kCommThreadsMax)
 k_barrier_only(const CommPtrs P, int rank, uint32_t *epoch_mem, int *err) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     peer_barrier<W>(P, rank, epoch_mem, 0, err);
     peer_barrier<W>(P, rank, epoch_mem, 1, err);
 }
@@ -279,25 +353,25 @@ static int launch_allreduce(int64_t off, int64_t n, float *m, float scale, float
     if (n == 0) return 0;
     const int64_t n4 = (n + 3) / 4;            // buffers are padded to 4 elements by the allocator
     B2_CHECK(off + n4 * 4 <= (c.n_elems + 3) / 4 * 4, B2_ERR_ARG, "comm: padded range exceeds buffer");
-    const int64_t cap = (int64_t)kCommBlocks * kCommThreads;
+    const int env_blocks = comm_blocks(), threads = comm_threads();
     bool oneshot;
     if (algo == 1) oneshot = true;
     else if (algo == 2) oneshot = false;
     else oneshot = (n * 4 * (int64_t)c.world <= ((int64_t)8 << 20));   // bytes each rank reads in one-shot mode
-    if (MODE == 0 && oneshot && n4 > cap) oneshot = false;
+    if (MODE == 0 && oneshot && n4 > (int64_t)kOneShotPerThread * env_blocks * threads) oneshot = false;
     if (c.world == 1) oneshot = true;
     // small messages: only as many blocks as there is data (same on every rank: a function of n)
-    int blocks = kCommBlocks;
-    if (oneshot) { int64_t need = (n4 + kCommThreads - 1) / kCommThreads; if (need < blocks) blocks = need < 1 ? 1 : (int)need; }
+    int blocks = env_blocks;            // two-shot kernels stride over their slice, so any grid <= kCommBlocks works (same on every rank)
+    if (oneshot) { int64_t need = (n4 + threads - 1) / threads; if (need < blocks) blocks = need < 1 ? 1 : (int)need; }
     const bool nvls = c.use_nvls && c.mc_grads && (MODE == 0 || c.mc_params) && c.world > 1;
 #define LAUNCH_W(Wv)                                                                                              \
-    if (nvls && oneshot) { B2_LAUNCH((k_allreduce_nvls<Wv, MODE, true>), blocks, kCommThreads, 0, s, c.ptrs, c.rank, c.mc_grads, c.mc_params, m, \
+    if (nvls && oneshot) { B2_LAUNCH((k_allreduce_nvls<Wv, MODE, true>), blocks, threads, 0, s, c.ptrs, c.rank, c.mc_grads, c.mc_params, m, \
                                      off, n4, scale, lr, momentum, first, mirror, c.epoch, c.err); }                  \
-    else if (nvls) { B2_LAUNCH((k_allreduce_nvls<Wv, MODE, false>), kCommBlocks, kCommThreads, 0, s, c.ptrs, c.rank, c.mc_grads, c.mc_params, m, \
+    else if (nvls) { B2_LAUNCH((k_allreduce_nvls<Wv, MODE, false>), blocks, threads, 0, s, c.ptrs, c.rank, c.mc_grads, c.mc_params, m, \
                                off, n4, scale, lr, momentum, first, mirror, c.epoch, c.err); }                        \
-    else if (oneshot) { B2_LAUNCH((k_allreduce<Wv, MODE, true>), blocks, kCommThreads, 0, s, c.ptrs, c.rank, m, off, n4, \
+    else if (oneshot) { B2_LAUNCH((k_allreduce<Wv, MODE, true>), blocks, threads, 0, s, c.ptrs, c.rank, m, off, n4, \
                              scale, lr, momentum, first, mirror, c.epoch, c.err); }                                   \
-    else { B2_LAUNCH((k_allreduce<Wv, MODE, false>), kCommBlocks, kCommThreads, 0, s, c.ptrs, c.rank, m, off, n4, scale,   \
+    else { B2_LAUNCH((k_allreduce<Wv, MODE, false>), blocks, threads, 0, s, c.ptrs, c.rank, m, off, n4, scale,   \
                      lr, momentum, first, mirror, c.epoch, c.err); }
     switch (c.world) {
     case 1: LAUNCH_W(1); break;
@@ -433,9 +507,9 @@ int b2_comm_barrier(void *stream) {
     B2_CHECK(c.inited && c.registered, B2_ERR_STATE, "comm: not initialised / no buffers registered");
     switch (c.world) {
     case 1: return 0;
-    case 2: B2_LAUNCH((k_barrier_only<2>), kCommBlocks, kCommThreads, 0, stream, c.ptrs, c.rank, c.epoch, c.err); break;
-    case 4: B2_LAUNCH((k_barrier_only<4>), kCommBlocks, kCommThreads, 0, stream, c.ptrs, c.rank, c.epoch, c.err); break;
-    case 8: B2_LAUNCH((k_barrier_only<8>), kCommBlocks, kCommThreads, 0, stream, c.ptrs, c.rank, c.epoch, c.err); break;
+    case 2: B2_LAUNCH((k_barrier_only<2>), comm_blocks(), comm_threads(), 0, stream, c.ptrs, c.rank, c.epoch, c.err); break;
+    case 4: B2_LAUNCH((k_barrier_only<4>), comm_blocks(), comm_threads(), 0, stream, c.ptrs, c.rank, c.epoch, c.err); break;
+    case 8: B2_LAUNCH((k_barrier_only<8>), comm_blocks(), comm_threads(), 0, stream, c.ptrs, c.rank, c.epoch, c.err); break;
     default: set_error("comm: world size %d not supported", c.world); return B2_ERR_UNSUPPORTED;
     }
     return 0;
@@ -460,3 +534,5 @@ int b2_allreduce_sgd_range(float *m, int64_t offset, int64_t n_elems, float lr, 
 }
 
 }  // extern "C"
+
+namespace b2 { B2_TRACE_INSTALLER(trace_install_comm) }

@@ -50,6 +50,45 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
 
+// ---- in-graph kernel trace (diagnostic; off unless b2_trace_start() installed a buffer) ----------------
+// Block 0 / thread 0 of a kernel appends (tag, %globaltimer) records: tag = TU id << 24 | source line << 4 | kind
+// (0 = past griddepcontrol.wait, 1 = end of block 0).  Works inside replayed CUDA graphs and on every stream, which
+// is what cudaEvents / ncu cannot show: what overlaps what in one real training step (tools/step_trace.py).
+// The symbols are per translation unit (no -rdc); B2_TRACE_TU defines that TU's id and its installer.
+static __device__ unsigned long long *d_trace_buf;
+static __device__ unsigned int *d_trace_cnt;
+static __device__ unsigned int d_trace_cap;
+#ifndef B2_TRACE_TU_ID
+#define B2_TRACE_TU_ID 0
+#endif
+__device__ __forceinline__ void trace_mark(int line, int kind) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
+        unsigned long long *buf = d_trace_buf;
+        if (buf) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            const unsigned int i = atomicAdd(d_trace_cnt, 1u);
+            if (i < d_trace_cap) {
+                buf[2 * i] = ((unsigned long long)B2_TRACE_TU_ID << 24) | ((unsigned long long)line << 4) | (unsigned)kind;
+                buf[2 * i + 1] = t;
+            }
+        }
+    }
+}
+#define B2_TRACE_BEGIN() b2::trace_mark(__LINE__, 0)
+#define B2_TRACE_END() b2::trace_mark(__LINE__, 1)
+#define B2_TRACE_INSTALLER(name)                                                                     \
+    int name(unsigned long long *buf, unsigned int *cnt, unsigned int cap) {                           \
+        if (cudaMemcpyToSymbol(d_trace_cnt, &cnt, sizeof(cnt)) != cudaSuccess) return B2_ERR_CUDA;     \
+        if (cudaMemcpyToSymbol(d_trace_cap, &cap, sizeof(cap)) != cudaSuccess) return B2_ERR_CUDA;     \
+        if (cudaMemcpyToSymbol(d_trace_buf, &buf, sizeof(buf)) != cudaSuccess) return B2_ERR_CUDA;     \
+        return 0;                                                                                      \
+    }
+int trace_install_comm(unsigned long long *buf, unsigned int *cnt, unsigned int cap);
+int trace_install_simt(unsigned long long *buf, unsigned int *cnt, unsigned int cap);
+int trace_install_umma(unsigned long long *buf, unsigned int *cnt, unsigned int cap);
+int trace_install_elem(unsigned long long *buf, unsigned int *cnt, unsigned int cap);
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                                 unsigned cluster_x, Args &&...args) {

@@ -7,6 +7,7 @@
 //
 // All three are C[M][N] (+)= sum_k A(m,k) * B(k,n) with 64x64x16 tiles, 256 threads,
 // 4x4 micro-tiles, operands gathered on the fly (no materialised im2col).
+#define B2_TRACE_TU_ID 2
 #include "ops.cuh"
 
 namespace b2 {
@@ -32,7 +33,7 @@ struct SimtArgs {
 template <int MODE, typename TA, typename TW, typename TC>
 __global__ void __launch_bounds__(256)
 k_conv_simt(const SimtArgs p) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
     const ConvGeom &g = p.g;
@@ -210,7 +211,7 @@ k_conv_simt(const SimtArgs p) {
 }
 
 __global__ void k_reduce_partials(const float *__restrict__ part, float *__restrict__ out, int64_t n, int splits) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float s = 0.f;
         for (int z = 0; z < splits; ++z) s += part[(int64_t)z * n + i];
@@ -291,3 +292,5 @@ int conv_simt_wgrad(const ConvGeom &g, const void *x, const void *dy, int dt, fl
 }
 
 }  // namespace b2
+
+namespace b2 { B2_TRACE_INSTALLER(trace_install_simt) }

@@ -24,6 +24,7 @@
 #include <mutex>
 #include <algorithm>
 #include <stdlib.h>
+#define B2_TRACE_TU_ID 3
 #include "conv_umma.cuh"
 #include "umma.cuh"
 
@@ -257,7 +258,7 @@ k_conv(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtens
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) TL(1);
-    pdl_wait();                    // everything below touches global memory of earlier kernels
+    pdl_wait(); B2_TRACE_BEGIN();                    // everything below touches global memory of earlier kernels
     if (threadIdx.x == 0) TL(2);
 
     if (STEM && warp >= 3 + kEpiWarps) {
@@ -581,6 +582,7 @@ k_conv(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtens
     }
     __syncthreads();
     if (threadIdx.x == 0) TL(12);
+    B2_TRACE_END();
 #undef TL
     if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
 }
@@ -628,7 +630,7 @@ k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUten
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();
+    pdl_wait(); B2_TRACE_BEGIN();
 
     if (warp == 0) {
         // ---- TMA producer: dY boxes (the two producers' streams overlap in the TMA unit)
@@ -738,6 +740,7 @@ k_wgrad(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUten
         tc_fence_before();
     }
     __syncthreads();
+    B2_TRACE_END();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
@@ -935,7 +938,7 @@ int umma_plan_wgrad(const ConvGeom &g, const bf16 *x, const bf16 *dy, float *dw,
 
 // dW[co][tap_id*Ci + c] = sum_z partial[z][co][a*Ci + c]   (a = live-tap index), float4 lanes
 __global__ void k_wgrad_reduce(const float *__restrict__ part, float *__restrict__ dw, WgradParams p) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     const int akc = p.out_pitch;                 // live taps * Ci
     const int64_t per_split = (int64_t)p.Co * akc;
     const int64_t n4 = per_split >> 2;
@@ -976,3 +979,5 @@ int umma_wgrad_launch(const UmmaWgradPlan &plan, cudaStream_t s) {
 }
 
 }  // namespace b2
+
+namespace b2 { B2_TRACE_INSTALLER(trace_install_umma) }

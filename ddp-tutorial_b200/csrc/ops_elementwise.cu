@@ -7,6 +7,7 @@
 //   cross_entropy (mean)      : cifar_example_ddp.py:85,105  (functional.py:3421-3504)
 //   SGD momentum              : cifar_example_ddp.py:86,107  (sgd.py:_single_tensor_sgd)
 #include <stdlib.h>
+#define B2_TRACE_TU_ID 4
 #include "ops.cuh"
 
 namespace b2 {
@@ -27,7 +28,7 @@ static inline int grid_for(int64_t n, int block, int max_blocks = kNumSMs * 16) 
 // ---------------------------------------------------------------------------------
 template <typename T>
 __global__ void k_nchw_to_nhwc(const float *__restrict__ x, T *__restrict__ y, int N, int C, int H, int W) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     int64_t total = (int64_t)N * C * H * W;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = i % C; int64_t r = i / C;
@@ -43,7 +44,7 @@ int op_nchw_to_nhwc(const float *x, void *y, int dt, int N, int C, int H, int W,
 }
 template <typename T>
 __global__ void k_nhwc_to_nchw(const T *__restrict__ x, float *__restrict__ y, int N, int C, int H, int W) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     int64_t total = (int64_t)N * C * H * W;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int w = i % W; int64_t r = i / W;
@@ -58,7 +59,7 @@ int op_nhwc_to_nchw_f32(const void *x, int dt, float *y, int N, int C, int H, in
     return 0;
 }
 __global__ void k_f32_to_bf16(const float *__restrict__ x, bf16 *__restrict__ y, int64_t n) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         y[i] = __float2bfloat16_rn(x[i]);
 }
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(256)
 k_bn_reduce(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy,
             const float *__restrict__ mean, const float *__restrict__ invstd, bool relu,
             int64_t M, int C, float *__restrict__ partial) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     // FWD: partial = {sum x, sum x^2};  BWD: partial = {sum g, sum g*xhat}
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(128)
 k_bn_finalize_fwd(const float *__restrict__ partial, int nblk, int64_t M, int C, float eps,
                   float momentum, float *__restrict__ mean, float *__restrict__ invstd,
                   float *running_mean, float *running_var) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
     double s0 = 0.0, s1 = 0.0;
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(256)
 k_bn_apply(const T *__restrict__ x, T *__restrict__ y, const T *__restrict__ res,
            const float *__restrict__ mean, const float *__restrict__ invstd,
            const float *__restrict__ gamma, const float *__restrict__ beta, bool relu, int64_t total, int C) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * V; i < total; i += (int64_t)gridDim.x * blockDim.x * V) {
         int c0 = i % C;
         __align__(16) T xv[V], rv[V], ov[V];
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(128)
 k_bn_finalize_bwd(const float *__restrict__ partial, int nblk, int64_t M, int C,
                   const float *__restrict__ gamma, const float *__restrict__ invstd,
                   float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
     double s0 = 0.0, s1 = 0.0;
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(256)
 k_bn_bwd_apply(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy, T *__restrict__ dx,
                T *__restrict__ dres, const float *__restrict__ mean, const float *__restrict__ invstd,
                const float *__restrict__ coef, bool relu, bool acc_dx, bool acc_dres, int64_t total, int C) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * V; i < total; i += (int64_t)gridDim.x * blockDim.x * V) {
         int c0 = i % C;
         __align__(16) T xv[V], yv[V], gv[V], ov[V], rv[V], pv[V];
@@ -267,7 +268,7 @@ int op_bn_backward(const void *x, const void *y, const void *dy, void *dx, void 
 template <typename T>
 __global__ void k_maxpool_fwd(const T *__restrict__ x, T *__restrict__ y, uint8_t *__restrict__ idx, int N, int Hi,
                               int Wi, int C, int k, int stride, int pad, int Ho, int Wo, bool out_nchw) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     int64_t total = (int64_t)N * Ho * Wo * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = i % C; int64_t r = i / C;
@@ -299,7 +300,7 @@ int op_maxpool_forward(const void *x, void *y, uint8_t *idx, int dt, int N, int 
 template <typename T>
 __global__ void k_maxpool_bwd(const T *__restrict__ dy, const uint8_t *__restrict__ idx, T *__restrict__ dx, int N,
                               int Hi, int Wi, int C, int k, int stride, int pad, int Ho, int Wo, bool out_nchw, bool acc) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     int64_t total = (int64_t)N * Hi * Wi * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = i % C; int64_t r = i / C;
@@ -334,7 +335,7 @@ int op_maxpool_backward(const void *dy, const uint8_t *idx, void *dx, int dt, in
 
 template <typename T>
 __global__ void k_avgpool_fwd(const T *__restrict__ x, float *__restrict__ y, int N, int HW, int C) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     int64_t total = (int64_t)N * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = i % C; int64_t n = i / C;
@@ -349,7 +350,7 @@ int op_avgpool_forward(const void *x, int xdt, float *y, int N, int HW, int C, c
 }
 template <typename T>
 __global__ void k_avgpool_bwd(const float *__restrict__ dy, T *__restrict__ dx, int N, int HW, int C, bool acc) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     int64_t total = (int64_t)N * HW * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = i % C; int64_t n = i / ((int64_t)HW * C);
@@ -368,7 +369,7 @@ int op_avgpool_backward(const float *dy, void *dx, int xdt, int N, int HW, int C
 // ---------------------------------------------------------------------------------
 template <typename T>
 __global__ void k_relu_mask(const T *__restrict__ y, T *__restrict__ dy, int64_t n) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         if (!(to_f<T>(y[i]) > 0.f)) dy[i] = from_f<T>(0.f);
 }
@@ -379,7 +380,7 @@ int op_relu_mask(const void *y, void *dy, int dt, int64_t n, cudaStream_t s) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_bias_grad(const T *__restrict__ dy, int64_t M, int C, float *__restrict__ db) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
     float s = 0.f;
@@ -411,7 +412,7 @@ constexpr int kCeRows = 512;
 __global__ void __launch_bounds__(kCeRows)
 k_ce_loss_grad(const float *__restrict__ logits, const int64_t *__restrict__ labels, int B, int C, int tile_rows,
                float *__restrict__ loss, float *__restrict__ dlogits, float *__restrict__ running) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     extern __shared__ float tile[];                 // [tile_rows][C], tile_rows <= kCeRows
     __shared__ float sh[kCeRows / 32];
     float local = 0.f;
@@ -470,7 +471,7 @@ int op_ce_loss_grad(const float *logits, const int64_t *labels, int B, int C, fl
 __global__ void __launch_bounds__(256)
 k_sgd(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, int64_t n, float lr, float mom,
       float gscale, int first, bf16 *__restrict__ pb) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     int64_t n4 = n >> 2;
     float4 *p4 = (float4 *)p; const float4 *g4 = (const float4 *)g; float4 *m4 = (float4 *)m;
     // torch semantics (sgd.py:_single_tensor_sgd): buf.mul_(momentum).add_(grad) is two
@@ -498,6 +499,7 @@ k_sgd(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
         m[i] = mv; float pn = fmaf(-lr, mv, p[i]); p[i] = pn;
         if (pb) pb[i] = __float2bfloat16_rn(pn);
     }
+    B2_TRACE_END();
 }
 int op_sgd(float *p, const float *g, float *m, int64_t n, float lr, float momentum, float gscale, int first, bf16 *pb,
            cudaStream_t s) {
@@ -527,7 +529,7 @@ template <int KK, int SS, int PP>        // compile-time window / stride / pad (
 __global__ void __launch_bounds__(256)
 k_maxpool_fwd_bf16x8(const bf16 *__restrict__ x, bf16 *__restrict__ y, uint8_t *__restrict__ idx, int N, int Hi, int Wi,
                      int C, int k_, int stride_, int pad_, int Ho, int Wo) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     const int k = KK ? KK : k_, stride = KK ? SS : stride_, pad = KK ? PP : pad_;
     const int C8 = C >> 3;
     const int64_t total = (int64_t)N * Ho * Wo * C8;
@@ -573,7 +575,7 @@ template <int KK, int SS, int PP>
 __global__ void __launch_bounds__(256)
 k_maxpool_bwd_bf16x8(const bf16 *__restrict__ dy, const uint8_t *__restrict__ idx, bf16 *__restrict__ dx, int N, int Hi,
                      int Wi, int C, int k_, int stride_, int pad_, int Ho, int Wo, bool acc) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     const int k = KK ? KK : k_, stride = KK ? SS : stride_, pad = KK ? PP : pad_;
     const int C8 = C >> 3;
     const int64_t total = (int64_t)N * Hi * Wi * C8;
@@ -628,7 +630,7 @@ template <int KS, int CH>
 __global__ void __launch_bounds__(256)
 k_stem_im2col(const float *__restrict__ x, bf16 *__restrict__ col, int N, int H, int W, int stride, int pad,
               int Ho, int Wo, int kpad) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     static_assert(KS <= 8, "one filter row per 8-wide chunk");
     extern __shared__ float simg[];                 // [CH][H][W + 1]: odd row pitch, lanes on different rows hit different banks
     const int n = blockIdx.x;
@@ -665,7 +667,7 @@ int op_stem_im2col(const float *x_nchw, bf16 *col, int N, int C, int H, int W, i
 }
 
 __global__ void k_stem_pack_weights(const float *__restrict__ m, bf16 *__restrict__ w, int Co, int C, int k, int kpad) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     const int total = Co * kpad;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int co = i / kpad, kk = i - co * kpad;
@@ -681,7 +683,7 @@ int op_stem_pack_weights(const float *master, bf16 *wpad, int Co, int C, int k, 
     return 0;
 }
 __global__ void k_stem_unpack_wgrad(const float *__restrict__ dwpad, float *__restrict__ g, int Co, int C, int k, int kpad) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     const int K = k * k * C, total = Co * K;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int co = i / K, r = i - co * K;
@@ -702,7 +704,7 @@ template <int NMAX>
 __global__ void __launch_bounds__(256)
 k_fc_fwd(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias, float *__restrict__ y,
          int B, int K, int N, bool relu) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     constexpr int KC = 512;
     __shared__ float sw[NMAX * KC];
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -746,7 +748,7 @@ int op_fc_forward(const float *x, const float *w, const float *bias, float *y, i
 __global__ void __launch_bounds__(256)
 k_fc_wgrad(const float *__restrict__ x, const float *__restrict__ dy, float *__restrict__ dw, float *__restrict__ db,
            int B, int K, int N) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int kk = blockIdx.x * 32 + tx, n = blockIdx.y;
     float s = 0.f, sb = 0.f;
@@ -774,7 +776,7 @@ k_fc_wgrad(const float *__restrict__ x, const float *__restrict__ dy, float *__r
 }
 __global__ void __launch_bounds__(256)
 k_fc_dgrad(const float *__restrict__ w, const float *__restrict__ dy, float *__restrict__ dx, int B, int K, int N, bool acc) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     const int64_t total = (int64_t)B * K;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int kk = i % K; int64_t b = i / K;
@@ -791,7 +793,7 @@ template <typename T, int NMAX>
 __global__ void __launch_bounds__(256)
 k_head_fwd(const T *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias, float *__restrict__ feat,
            float *__restrict__ y, int B, int HW, int C, int N) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     // The weight rows are C*4 bytes apart (2 KB for ResNet-18): read straight from global, the N rows of one channel
     // block collide in the L1 sets and every access goes to L2 (measured 28-47 us for this 5 MFLOP layer).  So the
     // block first copies W [N][C] into shared memory with coalesced 16-byte loads; then one warp per image, lanes over
@@ -861,7 +863,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_head_dgrad(const float *__restrict__ w, const float *__restrict__ dy, float *__restrict__ dfeat, T *__restrict__ dx, int B, int HW,
              int C, int N, bool acc) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     const int64_t total = (int64_t)B * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = i % C; const int64_t b = i / C;
@@ -904,7 +906,7 @@ k_bn_apply_fused(const T *__restrict__ x, T *__restrict__ y, const T *__restrict
                  int64_t M, const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ save_mean,
                  float *__restrict__ save_invstd, float *running_mean, float *running_var, float eps, float momentum,
                  bool relu, int64_t total, int C) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     extern __shared__ float sm[];             // scale[C], shift[C]
     float *scale = sm, *shift = sm + C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -949,18 +951,46 @@ int op_bn_forward_fused(const void *x, void *y, const void *res, int dt, int64_t
                         float momentum, bool relu, const BnWork &w, cudaStream_t s) {
     B2_CHECK(dt == DT_BF16 && C % 8 == 0, B2_ERR_ARG, "bn fused: bf16 activations with C %% 8 == 0 only");
     int64_t total = M * C;
+    B2_CHECK(total < ((int64_t)1 << 32), B2_ERR_UNSUPPORTED, "bn fused: tensor of %lld elements (32-bit indexing)", (long long)total);
     int64_t blocks = ceil_div(total / 8, 256); if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
     B2_LAUNCH((k_bn_apply_fused<bf16, 8>), (int)blocks, 256, 2 * C * sizeof(float), s, (const bf16 *)x, (bf16 *)y, (const bf16 *)res,
               fsum, M, gamma, beta, w.mean, w.invstd, running_mean, running_var, eps, momentum, relu, total, C);
     return 0;
 }
 
-template <typename T>
+// Gradient of a 3x3 / stride-2 / pad-1 max pooling's INPUT, recomputed from the pooled gradient and the argmax bytes
+// (same arithmetic as k_maxpool_bwd_bf16x8<3,2,1>): lets the BatchNorm backward in front of the pooling read its
+// upstream gradient without a max-pool-backward kernel and without the 2 x 16.8 MB gradient tensor in between.
+__device__ __forceinline__ void pool_grad8(const PoolGradSrc &P, int64_t row, int c0, int C, bf16 out[8]) {
+    const unsigned r32 = (unsigned)row;                         // Hi, Wi are powers of two (checked by the planner): no division
+    const int wi = (int)(r32 & (unsigned)(P.Wi - 1));
+    const int hi = (int)((r32 >> P.lgW) & (unsigned)(P.Hi - 1));
+    const int n = (int)(r32 >> (P.lgW + P.lgH));
+    float g[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = 0.f;
+    const int oh_lo = hi >> 1; int oh_hi = (hi + 1) >> 1; if (oh_hi > P.Ho - 1) oh_hi = P.Ho - 1;
+    const int ow_lo = wi >> 1; int ow_hi = (wi + 1) >> 1; if (ow_hi > P.Wo - 1) ow_hi = P.Wo - 1;
+    for (int oh = oh_lo; oh <= oh_hi; ++oh)
+        for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+            const int mine = (hi - (oh * 2 - 1)) * 3 + (wi - (ow * 2 - 1));
+            const unsigned o = ((unsigned)(n * P.Ho + oh) * (unsigned)P.Wo + (unsigned)ow) * (unsigned)C + (unsigned)c0;
+            const uint2 iraw = *(const uint2 *)(P.idx + o);
+            const uint4 draw = *(const uint4 *)(P.dpool + o);
+            const uint8_t *ix = (const uint8_t *)&iraw; const bf16 *dv = (const bf16 *)&draw;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) if (ix[e] == mine) g[e] += __bfloat162float(dv[e]);
+        }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[e] = __float2bfloat16_rn(g[e]);     // the rounding the materialised tensor had
+}
+
+template <typename T, bool POOL>
 __global__ void __launch_bounds__(256)
 k_bn_bwd_reduce_atomic(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy,
                        const float *__restrict__ mean, const float *__restrict__ invstd, bool relu, int64_t M, int C,
-                       int opb /* channel octets per block: min(C/8, 32) */, float *__restrict__ bsum) {
-    pdl_sync();
+                       int opb /* channel octets per block: min(C/8, 32) */, float *__restrict__ bsum, const PoolGradSrc pool) {
+    pdl_sync(); B2_TRACE_BEGIN();
     // each thread owns 8 consecutive channels (16-byte loads); 256/opb row lanes per block
     const int tx = threadIdx.x % opb, ty = threadIdx.x / opb, lanes = 256 / opb;
     const int c0 = (blockIdx.x * opb + tx) * 8;
@@ -970,16 +1000,28 @@ k_bn_bwd_reduce_atomic(const T *__restrict__ x, const T *__restrict__ y, const T
     float s0[8], s1[8], mu[8], is[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s0[e] = 0.f; s1[e] = 0.f; mu[e] = mean[c0 + e]; is[e] = invstd[c0 + e]; }
-    for (int64_t r = r0 + ty; r < r1; r += lanes) {
-        __align__(16) T xv[8], yv[8], gv[8];
-        *(uint4 *)xv = *(const uint4 *)(x + r * C + c0);
-        *(uint4 *)gv = *(const uint4 *)(dy + r * C + c0);
-        if (relu) *(uint4 *)yv = *(const uint4 *)(y + r * C + c0);
+    constexpr int RU = 2;                      // rows in flight per thread (the loop is latency-bound otherwise)
+    for (int64_t rb = r0 + ty; rb < r1; rb += lanes * RU) {
+        __align__(16) T xv[RU][8], yv[RU][8], gv[RU][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float g = to_f<T>(gv[e]);
-            if (relu && !(to_f<T>(yv[e]) > 0.f)) g = 0.f;
-            s0[e] += g; s1[e] += g * ((to_f<T>(xv[e]) - mu[e]) * is[e]);
+        for (int u = 0; u < RU; ++u) {
+            const int64_t r = rb + (int64_t)u * lanes;
+            if (r < r1) {
+                *(uint4 *)xv[u] = *(const uint4 *)(x + r * C + c0);
+                if (POOL) pool_grad8(pool, r, c0, C, (bf16 *)gv[u]);
+                else *(uint4 *)gv[u] = *(const uint4 *)(dy + r * C + c0);
+                if (relu) *(uint4 *)yv[u] = *(const uint4 *)(y + r * C + c0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            if (rb + (int64_t)u * lanes >= r1) break;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float g = to_f<T>(gv[u][e]);
+                if (relu && !(to_f<T>(yv[u][e]) > 0.f)) g = 0.f;
+                s0[e] += g; s1[e] += g * ((to_f<T>(xv[u][e]) - mu[e]) * is[e]);
+            }
         }
     }
     __shared__ float sh[256 * 17];
@@ -1005,13 +1047,14 @@ k_bn_bwd_reduce_atomic(const T *__restrict__ x, const T *__restrict__ y, const T
     }
 }
 
-template <typename T, int V>
+template <typename T, int V, bool POOL>
 __global__ void __launch_bounds__(256)
 k_bn_bwd_apply_fused(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy, T *__restrict__ dx,
                      T *__restrict__ dres, const float *__restrict__ mean, const float *__restrict__ invstd,
                      const float *__restrict__ bsum, const float *__restrict__ gamma, float *__restrict__ dgamma,
-                     float *__restrict__ dbeta, int64_t M, bool relu, bool acc_dx, bool acc_dres, int64_t total, int C) {
-    pdl_sync();
+                     float *__restrict__ dbeta, int64_t M, bool relu, bool acc_dx, bool acc_dres, int64_t total, int C,
+                     const PoolGradSrc pool) {
+    pdl_sync(); B2_TRACE_BEGIN();
     extern __shared__ float sm[];     // a[C], b[C], k[C]: dx = a*g + b*x + k   (per channel)
     float *ca = sm, *cb = sm + C, *ck = sm + 2 * C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -1026,10 +1069,11 @@ k_bn_bwd_apply_fused(const T *__restrict__ x, const T *__restrict__ y, const T *
     }
     __syncthreads();
     for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * V; i < total; i += (int64_t)gridDim.x * blockDim.x * V) {
-        int c0 = i % C;
+        const int c0 = (int)((unsigned)i % (unsigned)C);      // total < 2^32 (host check): 32-bit division
         __align__(16) T xv[V], yv[V], gv[V], ov[V], rv[V], pv[V];
         *(uint4 *)xv = *(const uint4 *)(x + i);
-        *(uint4 *)gv = *(const uint4 *)(dy + i);
+        if (POOL) pool_grad8(pool, (int64_t)((unsigned)i / (unsigned)C), c0, C, (bf16 *)gv);
+        else *(uint4 *)gv = *(const uint4 *)(dy + i);
         if (relu) *(uint4 *)yv = *(const uint4 *)(y + i);
         if (acc_dx) *(uint4 *)pv = *(const uint4 *)(dx + i);
         if (dres && acc_dres) *(uint4 *)rv = *(const uint4 *)(dres + i);
@@ -1060,7 +1104,7 @@ k_bn_bwd_small(const T *__restrict__ x, const T *__restrict__ y, const T *__rest
                T *__restrict__ dres, const float *__restrict__ mean, const float *__restrict__ invstd,
                const float *__restrict__ gamma, float *__restrict__ dgamma, float *__restrict__ dbeta, int64_t M, int C,
                bool relu, bool acc_dx, bool acc_dres) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     const int c0 = blockIdx.x * 8;
     float s0[8], s1[8], mu[8], is[8];
 #pragma unroll
@@ -1123,9 +1167,11 @@ k_bn_bwd_small(const T *__restrict__ x, const T *__restrict__ y, const T *__rest
 
 int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx, void *dres, int dt, int64_t M, int C,
                          float *bsum, const float *gamma, float *dgamma, float *dbeta, bool relu, bool acc_dx,
-                         bool acc_dres, bool sums_ready, const BnWork &w, cudaStream_t s) {
+                         bool acc_dres, bool sums_ready, const BnWork &w, const PoolGradSrc *pool, cudaStream_t s) {
     B2_CHECK(dt == DT_BF16 && C % 8 == 0, B2_ERR_ARG, "bn fused: bf16 activations with C %% 8 == 0 only");
-    if (!sums_ready && M <= 1024 && C >= 512) {      // measured (r01): wins only for the 1x1-spatial stage
+    B2_CHECK(!pool || (!sums_ready && !dres), B2_ERR_ARG, "bn fused: the pooled-gradient source excludes fused sums / a residual");
+    const PoolGradSrc pg = pool ? *pool : PoolGradSrc{nullptr, nullptr, 0, 0, 0, 0, 0, 0};
+    if (!pool && !sums_ready && M <= 1024 && C >= 512) {      // measured (r01): wins only for the 1x1-spatial stage
         B2_LAUNCH((k_bn_bwd_small<bf16>), C / 8, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, (bf16 *)dx,
                   (bf16 *)dres, w.mean, w.invstd, gamma, dgamma, dbeta, M, C, relu, acc_dx, acc_dres);
         return 0;
@@ -1136,17 +1182,26 @@ int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx,
         B2_CHECK((C / 8) % opb == 0 && 256 % opb == 0, B2_ERR_ARG, "bn fused: unsupported channel count %d", C);
         int gx = (C / 8) / opb;
         int lanes = 256 / opb;
-        int64_t want = (kNumSMs * 2 + gx - 1) / gx;
+        static const int mult = [] { const char *e = getenv("B2_BN_GRID_MULT"); int v = e ? atoi(e) : 0; return v > 0 ? v : 2; }();
+        int64_t want = (kNumSMs * (M * C >= (4 << 20) ? mult : 2) + gx - 1) / gx;
         int64_t maxb = ceil_div(M, (int64_t)lanes * 4); if (want > maxb) want = maxb; if (want < 1) want = 1;
         dim3 grid(gx, (unsigned)want);
-        B2_LAUNCH((k_bn_bwd_reduce_atomic<bf16>), grid, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, w.mean, w.invstd,
-                  relu, M, C, opb, bsum);
+        if (pool) { B2_LAUNCH((k_bn_bwd_reduce_atomic<bf16, true>), grid, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, w.mean,
+                              w.invstd, relu, M, C, opb, bsum, pg); }
+        else { B2_LAUNCH((k_bn_bwd_reduce_atomic<bf16, false>), grid, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, w.mean,
+                         w.invstd, relu, M, C, opb, bsum, pg); }
     }
     int64_t total = M * C;
-    int64_t blocks = ceil_div(total / 8, 256); if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
-    B2_LAUNCH((k_bn_bwd_apply_fused<bf16, 8>), (int)blocks, 256, 3 * C * sizeof(float), s, (const bf16 *)x, (const bf16 *)y,
-              (const bf16 *)dy, (bf16 *)dx, (bf16 *)dres, w.mean, w.invstd, bsum, gamma, dgamma, dbeta, M, relu, acc_dx, acc_dres,
-              total, C);
+    B2_CHECK(total < ((int64_t)1 << 32), B2_ERR_UNSUPPORTED, "bn fused: tensor of %lld elements (32-bit indexing)", (long long)total);
+    static const int amult = [] { const char *e = getenv("B2_BN_GRID_MULT"); int v = e ? atoi(e) : 0; return v > 0 ? v : 2; }();
+    const int64_t bcap = (int64_t)kNumSMs * (total >= (4 << 20) ? amult : 2);
+    int64_t blocks = ceil_div(total / 8, 256); if (blocks > bcap) blocks = bcap;
+    if (pool) { B2_LAUNCH((k_bn_bwd_apply_fused<bf16, 8, true>), (int)blocks, 256, 3 * C * sizeof(float), s, (const bf16 *)x, (const bf16 *)y,
+                          (const bf16 *)dy, (bf16 *)dx, (bf16 *)dres, w.mean, w.invstd, bsum, gamma, dgamma, dbeta, M, relu, acc_dx, acc_dres,
+                          total, C, pg); }
+    else { B2_LAUNCH((k_bn_bwd_apply_fused<bf16, 8, false>), (int)blocks, 256, 3 * C * sizeof(float), s, (const bf16 *)x, (const bf16 *)y,
+                     (const bf16 *)dy, (bf16 *)dx, (bf16 *)dres, w.mean, w.invstd, bsum, gamma, dgamma, dbeta, M, relu, acc_dx, acc_dres,
+                     total, C, pg); }
     return 0;
 }
 
@@ -1160,7 +1215,7 @@ namespace b2 {
 __global__ void __launch_bounds__(256)
 k_u8_to_normalized(const uint8_t *__restrict__ x, float *__restrict__ y, int N, int H, int W, int C, float m0, float m1, float m2,
                    float s0, float s1, float s2) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     const int64_t total = (int64_t)N * C * H * W;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int w = i % W; int64_t r = i / W;
@@ -1181,7 +1236,7 @@ int op_u8_to_normalized(const uint8_t *x, float *y, int N, int H, int W, int C, 
 
 __global__ void __launch_bounds__(256)
 k_argmax_count(const float *__restrict__ logits, const int64_t *__restrict__ labels, int B, int C, long long *counts) {
-    pdl_sync();
+    pdl_sync(); B2_TRACE_BEGIN();
     int correct = 0;
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         const float *row = logits + (int64_t)b * C;
@@ -1201,3 +1256,5 @@ int op_argmax_count(const float *logits, const int64_t *labels, int B, int C, lo
 }
 
 }  // namespace b2
+
+namespace b2 { B2_TRACE_INSTALLER(trace_install_elem) }

@@ -51,6 +51,12 @@ const char *b2_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's
  * gpu_launches claim); monotonically increasing. */
 int64_t b2_launch_count(void);
+/* Diagnostic kernel trace: while active, block 0 of every kernel of this library appends (tag, %globaltimer ns)
+ * records -- tag = translation unit << 24 | source line << 4 | kind (0 = kernel body begins, 1 = block 0 ends) --
+ * also inside replayed CUDA graphs and on the side streams (tools/step_trace.py turns them into a timeline).
+ * b2_trace_stop copies up to max_records (two uint64 each) to the host and switches the trace off. */
+int b2_trace_start(int capacity);
+int b2_trace_stop(unsigned long long *records, int max_records, int *n_out);
 
 /* ---- model: replaces Net()/resnetXX() + .to(gpu) (cifar_example_ddp.py:82) - */
 int b2_model_create(int kind, int batch, int num_classes, int precision, int device, b2_model **out);

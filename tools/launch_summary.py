@@ -12,7 +12,7 @@ for r in rd:
         if unit in ("us", "usecond"): v *= 1e3
         if unit in ("ms", "msecond"): v *= 1e6
         rows.append((r["Kernel Name"], v))
-starts = [i for i, (k, _) in enumerate(rows) if ("stem_im2col" in k or "nchw_to_nhwc" in k)]
+starts = [i for i, (k, _) in enumerate(rows) if ("stem_im2col" in k or "nchw_to_nhwc" in k or "k_stem_pack_weights" in k)]
 which = int(sys.argv[2]) if len(sys.argv) > 2 else -2
 a, b = starts[which], starts[which + 1]
 step = rows[a:b]
