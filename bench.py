@@ -432,7 +432,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 512 for resnet18, 256 for resnet50)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="DDP: one fused exchange at optimizer.step() instead of bucketed overlap")
-    ap.add_argument("--bucket-mb", type=float, default=16.0)
+    ap.add_argument("--bucket-mb", type=float, default=32.0)
     ap.add_argument("--no-clocks", action="store_true", help="skip the nvidia-smi sampler (profiler runs)")
     ap.add_argument("--no-parity", action="store_true", help="N>1: skip the DDP parity phase that runs before timing")
     ap.add_argument("--no-secondary", action="store_true", help="skip the ResNet-50 (BASELINE configs[3]) secondary measurement")

@@ -243,9 +243,6 @@ int b2_model_read_activation(b2_model *h, int op, int want_grad, float *out, int
     if (shape) { shape[0] = t.N; shape[1] = t.C; shape[2] = t.H; shape[3] = t.W; }
     if (!out) return 0;
     B2_CHECK(capacity >= t.numel, B2_ERR_ARG, "read_activation: capacity %lld < %lld", (long long)capacity, (long long)t.numel);
-    B2_CHECK(!(want_grad && o.type == OP_BN && o.bn_fused && o.pool_op >= 0), B2_ERR_UNSUPPORTED,
-             "read_activation: the gradient of op %d's output is never materialised (the max pooling's backward is recomputed "
-             "inside this BatchNorm's backward kernels; B2_FUSE_POOL_BWD=0 keeps the tensor)", op);
     const void *src = want_grad ? t.grad : t.val;
     if (o.type == OP_MAXPOOL && o.out_nchw) {   // already NCHW-flat
         B2_CHECK(t.dt == DT_F32, B2_ERR_UNSUPPORTED, "read_activation: flat bf16 tensor");

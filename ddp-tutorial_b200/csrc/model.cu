@@ -59,7 +59,7 @@ int64_t Model::add_mat(const std::string &name, int rows, int cols) {
 
 int Model::op_conv(int in, int64_t w_off, int64_t b_off, int Co, int k, int stride, int pad, bool relu, int out_dt) {
     const Tensor &ti = tensors[in];
-    Op o{}; o.pool_op = -1;
+    Op o{};
     o.type = OP_CONV; o.in = in; o.res = -1;
     o.g.N = ti.N; o.g.Hi = ti.H; o.g.Wi = ti.W; o.g.Ci = ti.C;
     o.g.kh = o.g.kw = k; o.g.stride = stride; o.g.pad = pad;
@@ -71,7 +71,7 @@ int Model::op_conv(int in, int64_t w_off, int64_t b_off, int Co, int k, int stri
 }
 int Model::op_bn(int in, int64_t g_off, int64_t b_off, int64_t rm_off, int64_t rv_off, bool relu, int res) {
     const Tensor &ti = tensors[in];
-    Op o{}; o.pool_op = -1;
+    Op o{};
     o.type = OP_BN; o.in = in; o.res = res; o.relu = relu;
     o.w_off = g_off; o.b_off = b_off; o.rm_off = rm_off; o.rv_off = rv_off;
     o.out = add_tensor(ti.N, ti.H, ti.W, ti.C, ti.dt);
@@ -80,7 +80,7 @@ int Model::op_bn(int in, int64_t g_off, int64_t b_off, int64_t rm_off, int64_t r
 }
 int Model::op_maxpool(int in, int k, int stride, int pad, bool out_nchw_flat) {
     const Tensor &ti = tensors[in];
-    Op o{}; o.pool_op = -1;
+    Op o{};
     o.type = OP_MAXPOOL; o.in = in; o.res = -1;
     o.g.N = ti.N; o.g.Hi = ti.H; o.g.Wi = ti.W; o.g.Ci = ti.C; o.g.Co = ti.C;
     o.g.kh = o.g.kw = k; o.g.stride = stride; o.g.pad = pad;
@@ -93,7 +93,7 @@ int Model::op_maxpool(int in, int k, int stride, int pad, bool out_nchw_flat) {
 }
 int Model::op_avgpool(int in) {
     const Tensor &ti = tensors[in];
-    Op o{}; o.pool_op = -1;
+    Op o{};
     o.type = OP_AVGPOOL; o.in = in; o.res = -1;
     o.out = add_tensor(ti.N, 1, 1, ti.C, DT_F32);
     ops.push_back(o);
@@ -367,12 +367,7 @@ int Model::set_ddp(bool enable, float *mom, float lr, float momentum, int algo, 
     B2_CHECK(mom, B2_ERR_ARG, "set_ddp: NULL momentum buffer");
     ddp_mom = mom; ddp_lr = lr; ddp_momentum = momentum; ddp_algo = algo;
     if (!ddp_stream) {
-        // B2_DDP_PRIO=1: the exchange / optimizer kernels get the capture stream's (highest) priority, so that the
-        // block scheduler does not park them behind the early-launched (PDL) CTAs of the main chain
-        static const bool hi_prio = [] { const char *e = getenv("B2_DDP_PRIO"); return e && e[0] == '1'; }();
-        int lo = 0, hi = 0;
-        B2_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        B2_CUDA(cudaStreamCreateWithPriority(&ddp_stream, cudaStreamNonBlocking, hi_prio ? hi : lo));
+        B2_CUDA(cudaStreamCreateWithFlags(&ddp_stream, cudaStreamNonBlocking));
         B2_CUDA(cudaEventCreateWithFlags(&ddp_fork, cudaEventDisableTiming));
         B2_CUDA(cudaEventCreateWithFlags(&ddp_join, cudaEventDisableTiming));
     }
@@ -521,24 +516,6 @@ int Model::build_plans() {
                     b.fwd_in_conv = true;
                 }
             }
-        // a 3x3 / stride-2 max pooling as the ONLY consumer (the stem): its backward is recomputed inside this
-        // BatchNorm's backward kernels from the pooled gradient + argmax bytes (B2_FUSE_POOL_BWD=0 disables)
-        b.pool_op = -1;
-        {
-            static const bool enable = [] { const char *e = getenv("B2_FUSE_POOL_BWD"); return !(e && e[0] == '0'); }();
-            int consumers = 0, pi = -1;
-            for (size_t k = 0; k < ops.size(); ++k)
-                if (ops[k].in == b.out || ops[k].res == b.out) { ++consumers; pi = (int)k; }
-            if (enable && consumers == 1 && ops[pi].type == OP_MAXPOOL && ops[pi].in == b.out && b.res < 0) {
-                Op &pl = ops[pi];
-                const Tensor &tb = tensors[b.out];
-                if (pl.g.kh == 3 && pl.g.kw == 3 && pl.g.stride == 2 && pl.g.pad == 1 && tb.dt == DT_BF16 && tb.C % 8 == 0 &&
-                    !pl.out_nchw && !pl.acc_in && pl.need_dgrad && (pl.g.Hi & (pl.g.Hi - 1)) == 0 && (pl.g.Wi & (pl.g.Wi - 1)) == 0 &&
-                    tb.numel < ((int64_t)1 << 32)) {
-                    b.pool_op = pi; pl.bwd_in_bn = true;
-                }
-            }
-        }
         // last writer of d(b.out) in backward order = its first consumer in forward order
         b.bwd_sums_fused = false;
         for (Op &c : ops) {
@@ -851,19 +828,10 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
         case OP_BN: {
             int64_t M = (int64_t)ti.N * ti.H * ti.W;
             int ph = prof_begin(PC_BN_BWD, 0, ti.numel * (double)dt_size(ti.dt) * (o.res >= 0 ? 7.0 : 6.0), s);
-            if (o.bn_fused) {
-                PoolGradSrc pg{};
-                if (o.pool_op >= 0) {
-                    const Op &pl = ops[o.pool_op];
-                    int lgH = 0, lgW = 0;
-                    while ((1 << lgH) < pl.g.Hi) ++lgH;
-                    while ((1 << lgW) < pl.g.Wi) ++lgW;
-                    pg = PoolGradSrc{(const bf16 *)tensors[pl.out].grad, pl.idx, pl.g.Hi, pl.g.Wi, pl.g.Ho, pl.g.Wo, lgH, lgW};
-                }
+            if (o.bn_fused)
                 B2_TRY(op_bn_backward_fused(ti.val, to.val, to.grad, ti.grad, o.res >= 0 ? tensors[o.res].grad : nullptr, ti.dt, M,
                                             ti.C, o.bsum, p_params + o.w_off, p_grads + o.w_off, p_grads + o.b_off, o.relu,
-                                            o.acc_in, o.acc_res, o.bwd_sums_fused, o.bn, o.pool_op >= 0 ? &pg : nullptr, s));
-            }
+                                            o.acc_in, o.acc_res, o.bwd_sums_fused, o.bn, s));
             else
             B2_TRY(op_bn_backward(ti.val, to.val, to.grad, ti.grad, o.res >= 0 ? tensors[o.res].grad : nullptr, ti.dt, M,
                                   ti.C, p_params + o.w_off, p_grads + o.w_off, p_grads + o.b_off, o.relu, o.acc_in,
@@ -872,7 +840,6 @@ int Model::backward_impl(const float *dlogits, cudaStream_t s) {
             break;
         }
         case OP_MAXPOOL:
-            if (o.bwd_in_bn) break;          // recomputed inside the producing BatchNorm's backward (Op::pool_op)
             if (o.need_dgrad) {
                 if (ti.dt == DT_BF16 && !o.out_nchw && o.g.Ci % 8 == 0)
                     B2_TRY(op_maxpool_backward_bf16x8((const bf16 *)to.grad, o.idx, (bf16 *)ti.grad, o.g.N, o.g.Hi, o.g.Wi, o.g.Ci,

@@ -31,8 +31,6 @@ struct Op {
     unsigned int *fb_counter;    // [0] arrivals, [1] generation of the fused conv+BN grid barrier
     bool bwd_sums_fused;         // the dgrad that finalises this BN's output gradient also accumulates bsum
     uint8_t *idx;                // maxpool argmax
-    int pool_op;                 // bn: index of the 3x3/s2 max pooling whose backward is folded into this BatchNorm's backward (-1: none)
-    bool bwd_in_bn;              // maxpool: backward done by the producing BatchNorm's backward kernels
     int wdt, wpitch;             // conv: weight operand type / row pitch as the kernels see it
     bool use_umma;               // tcgen05 path (bf16, channel counts multiples of 64)
     bool is_fc;                  // small fp32 classifier head -> dedicated kernels

@@ -38,11 +38,9 @@ int op_bn_forward_fused(const void *x, void *y, const void *res, int dt, int64_t
                         const float *gamma, const float *beta, float *running_mean, float *running_var, float eps,
                         float momentum, bool relu, const BnWork &w, cudaStream_t s);
 // sums_ready: bsum was already accumulated by the dgrad that produced dy (skip the reduce pass)
-// pooled-gradient source for a BatchNorm that feeds a 3x3 / stride-2 / pad-1 max pooling (its dy is recomputed, not read)
-struct PoolGradSrc { const bf16 *dpool; const uint8_t *idx; int Hi, Wi, Ho, Wo, lgH, lgW; };   // Hi, Wi powers of two; N*Hi*Wi*C < 2^32
 int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx, void *dres, int dt, int64_t M, int C,
                          float *bsum, const float *gamma, float *dgamma, float *dbeta, bool relu, bool acc_dx,
-                         bool acc_dres, bool sums_ready, const BnWork &w, const PoolGradSrc *pool, cudaStream_t s);
+                         bool acc_dres, bool sums_ready, const BnWork &w, cudaStream_t s);
 
 // ---- pooling -------------------------------------------------------------------
 int op_maxpool_forward(const void *x, void *y, uint8_t *idx, int dt, int N, int Hi, int Wi, int C,

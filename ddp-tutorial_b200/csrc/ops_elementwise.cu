@@ -958,38 +958,11 @@ int op_bn_forward_fused(const void *x, void *y, const void *res, int dt, int64_t
     return 0;
 }
 
-// Gradient of a 3x3 / stride-2 / pad-1 max pooling's INPUT, recomputed from the pooled gradient and the argmax bytes
-// (same arithmetic as k_maxpool_bwd_bf16x8<3,2,1>): lets the BatchNorm backward in front of the pooling read its
-// upstream gradient without a max-pool-backward kernel and without the 2 x 16.8 MB gradient tensor in between.
-__device__ __forceinline__ void pool_grad8(const PoolGradSrc &P, int64_t row, int c0, int C, bf16 out[8]) {
-    const unsigned r32 = (unsigned)row;                         // Hi, Wi are powers of two (checked by the planner): no division
-    const int wi = (int)(r32 & (unsigned)(P.Wi - 1));
-    const int hi = (int)((r32 >> P.lgW) & (unsigned)(P.Hi - 1));
-    const int n = (int)(r32 >> (P.lgW + P.lgH));
-    float g[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) g[e] = 0.f;
-    const int oh_lo = hi >> 1; int oh_hi = (hi + 1) >> 1; if (oh_hi > P.Ho - 1) oh_hi = P.Ho - 1;
-    const int ow_lo = wi >> 1; int ow_hi = (wi + 1) >> 1; if (ow_hi > P.Wo - 1) ow_hi = P.Wo - 1;
-    for (int oh = oh_lo; oh <= oh_hi; ++oh)
-        for (int ow = ow_lo; ow <= ow_hi; ++ow) {
-            const int mine = (hi - (oh * 2 - 1)) * 3 + (wi - (ow * 2 - 1));
-            const unsigned o = ((unsigned)(n * P.Ho + oh) * (unsigned)P.Wo + (unsigned)ow) * (unsigned)C + (unsigned)c0;
-            const uint2 iraw = *(const uint2 *)(P.idx + o);
-            const uint4 draw = *(const uint4 *)(P.dpool + o);
-            const uint8_t *ix = (const uint8_t *)&iraw; const bf16 *dv = (const bf16 *)&draw;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) if (ix[e] == mine) g[e] += __bfloat162float(dv[e]);
-        }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) out[e] = __float2bfloat16_rn(g[e]);     // the rounding the materialised tensor had
-}
-
-template <typename T, bool POOL>
+template <typename T>
 __global__ void __launch_bounds__(256)
 k_bn_bwd_reduce_atomic(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy,
                        const float *__restrict__ mean, const float *__restrict__ invstd, bool relu, int64_t M, int C,
-                       int opb /* channel octets per block: min(C/8, 32) */, float *__restrict__ bsum, const PoolGradSrc pool) {
+                       int opb /* channel octets per block: min(C/8, 32) */, float *__restrict__ bsum) {
     pdl_sync(); B2_TRACE_BEGIN();
     // each thread owns 8 consecutive channels (16-byte loads); 256/opb row lanes per block
     const int tx = threadIdx.x % opb, ty = threadIdx.x / opb, lanes = 256 / opb;
@@ -1008,8 +981,7 @@ k_bn_bwd_reduce_atomic(const T *__restrict__ x, const T *__restrict__ y, const T
             const int64_t r = rb + (int64_t)u * lanes;
             if (r < r1) {
                 *(uint4 *)xv[u] = *(const uint4 *)(x + r * C + c0);
-                if (POOL) pool_grad8(pool, r, c0, C, (bf16 *)gv[u]);
-                else *(uint4 *)gv[u] = *(const uint4 *)(dy + r * C + c0);
+                *(uint4 *)gv[u] = *(const uint4 *)(dy + r * C + c0);
                 if (relu) *(uint4 *)yv[u] = *(const uint4 *)(y + r * C + c0);
             }
         }
@@ -1047,13 +1019,12 @@ k_bn_bwd_reduce_atomic(const T *__restrict__ x, const T *__restrict__ y, const T
     }
 }
 
-template <typename T, int V, bool POOL>
+template <typename T, int V>
 __global__ void __launch_bounds__(256)
 k_bn_bwd_apply_fused(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ dy, T *__restrict__ dx,
                      T *__restrict__ dres, const float *__restrict__ mean, const float *__restrict__ invstd,
                      const float *__restrict__ bsum, const float *__restrict__ gamma, float *__restrict__ dgamma,
-                     float *__restrict__ dbeta, int64_t M, bool relu, bool acc_dx, bool acc_dres, int64_t total, int C,
-                     const PoolGradSrc pool) {
+                     float *__restrict__ dbeta, int64_t M, bool relu, bool acc_dx, bool acc_dres, int64_t total, int C) {
     pdl_sync(); B2_TRACE_BEGIN();
     extern __shared__ float sm[];     // a[C], b[C], k[C]: dx = a*g + b*x + k   (per channel)
     float *ca = sm, *cb = sm + C, *ck = sm + 2 * C;
@@ -1072,8 +1043,7 @@ k_bn_bwd_apply_fused(const T *__restrict__ x, const T *__restrict__ y, const T *
         const int c0 = (int)((unsigned)i % (unsigned)C);      // total < 2^32 (host check): 32-bit division
         __align__(16) T xv[V], yv[V], gv[V], ov[V], rv[V], pv[V];
         *(uint4 *)xv = *(const uint4 *)(x + i);
-        if (POOL) pool_grad8(pool, (int64_t)((unsigned)i / (unsigned)C), c0, C, (bf16 *)gv);
-        else *(uint4 *)gv = *(const uint4 *)(dy + i);
+        *(uint4 *)gv = *(const uint4 *)(dy + i);
         if (relu) *(uint4 *)yv = *(const uint4 *)(y + i);
         if (acc_dx) *(uint4 *)pv = *(const uint4 *)(dx + i);
         if (dres && acc_dres) *(uint4 *)rv = *(const uint4 *)(dres + i);
@@ -1167,11 +1137,9 @@ k_bn_bwd_small(const T *__restrict__ x, const T *__restrict__ y, const T *__rest
 
 int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx, void *dres, int dt, int64_t M, int C,
                          float *bsum, const float *gamma, float *dgamma, float *dbeta, bool relu, bool acc_dx,
-                         bool acc_dres, bool sums_ready, const BnWork &w, const PoolGradSrc *pool, cudaStream_t s) {
+                         bool acc_dres, bool sums_ready, const BnWork &w, cudaStream_t s) {
     B2_CHECK(dt == DT_BF16 && C % 8 == 0, B2_ERR_ARG, "bn fused: bf16 activations with C %% 8 == 0 only");
-    B2_CHECK(!pool || (!sums_ready && !dres), B2_ERR_ARG, "bn fused: the pooled-gradient source excludes fused sums / a residual");
-    const PoolGradSrc pg = pool ? *pool : PoolGradSrc{nullptr, nullptr, 0, 0, 0, 0, 0, 0};
-    if (!pool && !sums_ready && M <= 1024 && C >= 512) {      // measured (r01): wins only for the 1x1-spatial stage
+    if (!sums_ready && M <= 1024 && C >= 512) {      // measured (r01): wins only for the 1x1-spatial stage
         B2_LAUNCH((k_bn_bwd_small<bf16>), C / 8, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, (bf16 *)dx,
                   (bf16 *)dres, w.mean, w.invstd, gamma, dgamma, dbeta, M, C, relu, acc_dx, acc_dres);
         return 0;
@@ -1182,26 +1150,18 @@ int op_bn_backward_fused(const void *x, const void *y, const void *dy, void *dx,
         B2_CHECK((C / 8) % opb == 0 && 256 % opb == 0, B2_ERR_ARG, "bn fused: unsupported channel count %d", C);
         int gx = (C / 8) / opb;
         int lanes = 256 / opb;
-        static const int mult = [] { const char *e = getenv("B2_BN_GRID_MULT"); int v = e ? atoi(e) : 0; return v > 0 ? v : 2; }();
-        int64_t want = (kNumSMs * (M * C >= (4 << 20) ? mult : 2) + gx - 1) / gx;
+        int64_t want = (kNumSMs * 2 + gx - 1) / gx;
         int64_t maxb = ceil_div(M, (int64_t)lanes * 4); if (want > maxb) want = maxb; if (want < 1) want = 1;
         dim3 grid(gx, (unsigned)want);
-        if (pool) { B2_LAUNCH((k_bn_bwd_reduce_atomic<bf16, true>), grid, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, w.mean,
-                              w.invstd, relu, M, C, opb, bsum, pg); }
-        else { B2_LAUNCH((k_bn_bwd_reduce_atomic<bf16, false>), grid, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, w.mean,
-                         w.invstd, relu, M, C, opb, bsum, pg); }
+        B2_LAUNCH((k_bn_bwd_reduce_atomic<bf16>), grid, 256, 0, s, (const bf16 *)x, (const bf16 *)y, (const bf16 *)dy, w.mean, w.invstd,
+                  relu, M, C, opb, bsum);
     }
     int64_t total = M * C;
     B2_CHECK(total < ((int64_t)1 << 32), B2_ERR_UNSUPPORTED, "bn fused: tensor of %lld elements (32-bit indexing)", (long long)total);
-    static const int amult = [] { const char *e = getenv("B2_BN_GRID_MULT"); int v = e ? atoi(e) : 0; return v > 0 ? v : 2; }();
-    const int64_t bcap = (int64_t)kNumSMs * (total >= (4 << 20) ? amult : 2);
-    int64_t blocks = ceil_div(total / 8, 256); if (blocks > bcap) blocks = bcap;
-    if (pool) { B2_LAUNCH((k_bn_bwd_apply_fused<bf16, 8, true>), (int)blocks, 256, 3 * C * sizeof(float), s, (const bf16 *)x, (const bf16 *)y,
-                          (const bf16 *)dy, (bf16 *)dx, (bf16 *)dres, w.mean, w.invstd, bsum, gamma, dgamma, dbeta, M, relu, acc_dx, acc_dres,
-                          total, C, pg); }
-    else { B2_LAUNCH((k_bn_bwd_apply_fused<bf16, 8, false>), (int)blocks, 256, 3 * C * sizeof(float), s, (const bf16 *)x, (const bf16 *)y,
-                     (const bf16 *)dy, (bf16 *)dx, (bf16 *)dres, w.mean, w.invstd, bsum, gamma, dgamma, dbeta, M, relu, acc_dx, acc_dres,
-                     total, C, pg); }
+    int64_t blocks = ceil_div(total / 8, 256); if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
+    B2_LAUNCH((k_bn_bwd_apply_fused<bf16, 8>), (int)blocks, 256, 3 * C * sizeof(float), s, (const bf16 *)x, (const bf16 *)y,
+              (const bf16 *)dy, (bf16 *)dx, (bf16 *)dres, w.mean, w.invstd, bsum, gamma, dgamma, dbeta, M, relu, acc_dx, acc_dres,
+              total, C);
     return 0;
 }
 

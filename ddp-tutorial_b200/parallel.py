@@ -218,7 +218,7 @@ class DistributedDataParallel:
     """
 
     def __init__(self, module, device_ids: Optional[List[int]] = None, algo: int = 0, overlap: bool = True,
-                 bucket_cap_mb: float = 16.0, nvls: Optional[bool] = None):
+                 bucket_cap_mb: float = 32.0, nvls: Optional[bool] = None):
         if not _state["distributed"]:
             raise B2Error("Default process group has not been initialized: call init_distributed(args) "
                           "under torchrun first (cifar_example_ddp.py:69)")

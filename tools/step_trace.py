@@ -1,6 +1,6 @@
 """In-graph timeline of ONE training step (b2_trace_start / b2_trace_stop, csrc/common.cuh:trace_mark).
 
-  python tools/step_trace.py [--model resnet18] [--batch 512] [--bucket-mb 4] [--out gpurun_out/trace.txt]
+  python tools/step_trace.py [--model resnet18] [--batch 512] [--bucket-mb 32] [--out gpurun_out/trace.txt]
   python -m torch.distributed.run --nproc-per-node 2 ... tools/step_trace.py      (every rank writes <out>.rank<r>)
 
 Each record is block 0 / thread 0 of a kernel passing griddepcontrol.wait ("begin") or finishing ("end", only the
@@ -32,7 +32,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="resnet18")
     ap.add_argument("--batch", type=int, default=512)
-    ap.add_argument("--bucket-mb", type=float, default=4.0)
+    ap.add_argument("--bucket-mb", type=float, default=32.0)
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--out", default="gpurun_out/step_trace.txt")
