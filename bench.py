@@ -171,7 +171,13 @@ def ddp_parity(b2, O, ns, model_name, batch, precision, dev, rank, world, overla
 
     init_same = replicas_identical()
     p0 = e.flat_params[:e.n_params].cpu().clone()
-    r = O.train(model_name, seed=0, batch=batch, steps=steps, world=world) if rank == 0 else None
+    r = None
+    if rank == 0:                                      # the oracle's world=N run on the host (torchrun pins OMP threads to 1)
+        nt = torch.get_num_threads()
+        torch.set_num_threads(usable_cores())
+        r = O.train(model_name, seed=0, batch=batch, steps=steps, world=world)
+        torch.set_num_threads(nt)
+    dist.barrier()                                     # (gloo) no rank enters the exchange kernels while rank 0 is still on the host
     xg, yg = O.synthetic_batch(O.data_generator(0), batch * world)
     x, y = xg[rank * batch:(rank + 1) * batch].to(dev), yg[rank * batch:(rank + 1) * batch].to(dev)
     losses = []

@@ -109,10 +109,12 @@ __device__ __forceinline__ void peer_barrier(const CommPtrs &P, int rank, uint32
         const uint32_t *mine = P.flags[rank] + ((phase * kMaxWorld + peer) * kFlagStride + blockIdx.x);
         long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
-            // ~20 s without the peer: a rank died or diverged.  Continuing would reduce stale data and let the
-            // replicas drift apart silently, so record the reason and kill the context (every later CUDA call
-            // on this rank fails loudly; b2_comm_check() reports the flag when the host polls first).
-            if (clock64() - t0 > 40000000000LL) { *err = 1; __threadfence_system(); __trap(); }
+            // ~2 min without the peer: a rank died or diverged (a rank that is merely late -- host-side work between
+            // steps -- must not trip this).  Continuing would reduce stale data and let the replicas drift apart
+            // silently, so record the reason and kill the context (every later CUDA call on this rank fails loudly;
+            // b2_comm_check() reports the flag when the host polls first).
+            if (clock64() - t0 > 230000000000LL) { *err = 1; __threadfence_system(); __trap(); }
+            __nanosleep(64);        // poll gently: the flag lives in local memory next to a training step's traffic
         }
     }
     __syncthreads();
