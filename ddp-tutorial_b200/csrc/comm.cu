@@ -36,10 +36,22 @@ static int comm_threads() {
                               return (t >= 32 && t <= kCommThreadsMax && t % 32 == 0) ? t : 512; }();
     return v;
 }
-static int comm_blocks() {
+static int comm_blocks_env() {          // 0 = not set
     static const int v = [] { const char *e = getenv("B2_COMM_BLOCKS"); int t = e ? atoi(e) : 0;
-                              return (t > 0 && t <= kCommBlocks) ? t : 96; }();
+                              return (t > 0 && t <= kCommBlocks) ? t : 0; }();
     return v;
+}
+// Grid of one exchange kernel.  A stand-alone all-reduce (MODE 0) wants the whole machine: 96 CTAs.  The fused
+// all-reduce + SGD of a gradient bucket (MODE 1) runs UNDER backward with hundreds of microseconds to spare, and every
+// SM that hosts one of its CTAs serves the latency-bound kernels beside it 2-10x slower (their loads queue behind
+// ~2000 outstanding NVLink requests per comm CTA; tools/step_trace.py showed single BatchNorm launches of 68 us instead
+// of 6.5 us).  Fewer CTAs = fewer slow SMs: measured step time at W=8 (NVLS, ResNet-18): 96 CTAs 0.996 ms, 64 0.995,
+// 48 0.984, 32 0.972, 24 0.960; at W=2: 96 0.977, 48 0.951 (profiles/r02_comm_shape_sweep.txt).  The slice a rank owns
+// shrinks with W, so the grid does too.
+static int comm_blocks(int mode, int world, bool nvls) {
+    if (comm_blocks_env()) return comm_blocks_env();
+    if (mode == 0 || !nvls) return 96;
+    return world <= 2 ? 48 : (world <= 4 ? 32 : 24);
 }
 // flag layout (uint32 words): [phase 0/1][src rank][block]
 constexpr int kFlagStride = kCommBlocks;
@@ -224,9 +236,12 @@ k_allreduce(const CommPtrs P, int rank, float *__restrict__ mom_buf, int64_t off
         peer_barrier<W>(P, rank, epoch_mem, 1, err);          // all slices have landed everywhere
         if (MODE == 1 && mirror) {
             // every replica now holds the full updated fp32 range: refresh the local bf16 mirror
-            for (int64_t i = tid; i < n4; i += stride) {
-                const int64_t e = off + i * 4;
-                st_bf16x4(mirror + e, ld_peer_f4(P.params[rank] + e));
+            for (int64_t i0 = tid; i0 < n4; i0 += stride * 4) {          // 4 loads in flight (the asm loads are volatile)
+                float4 pv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int64_t i = i0 + u * stride; if (i < n4) pv[u] = ld_peer_f4(P.params[rank] + off + i * 4); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int64_t i = i0 + u * stride; if (i < n4) st_bf16x4(mirror + off + i * 4, pv[u]); }
             }
         }
     }
@@ -326,9 +341,12 @@ k_allreduce_nvls(const CommPtrs P, int rank, float *__restrict__ mc_grads, float
         }
         peer_barrier<W>(P, rank, epoch_mem, 1, err);          // all slices have landed everywhere
         if (MODE == 1 && mirror) {
-            for (int64_t i = tid; i < n4; i += stride) {
-                const int64_t e = off + i * 4;
-                st_bf16x4(mirror + e, ld_peer_f4(P.params[rank] + e));
+            for (int64_t i0 = tid; i0 < n4; i0 += stride * 4) {          // 4 loads in flight (the asm loads are volatile)
+                float4 pv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int64_t i = i0 + u * stride; if (i < n4) pv[u] = ld_peer_f4(P.params[rank] + off + i * 4); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int64_t i = i0 + u * stride; if (i < n4) st_bf16x4(mirror + off + i * 4, pv[u]); }
             }
         }
     }
@@ -355,7 +373,9 @@ static int launch_allreduce(int64_t off, int64_t n, float *m, float scale, float
     if (n == 0) return 0;
     const int64_t n4 = (n + 3) / 4;            // buffers are padded to 4 elements by the allocator
     B2_CHECK(off + n4 * 4 <= (c.n_elems + 3) / 4 * 4, B2_ERR_ARG, "comm: padded range exceeds buffer");
-    const int env_blocks = comm_blocks(), threads = comm_threads();
+    const int threads = comm_threads();
+    const bool nvls = c.use_nvls && c.mc_grads && (MODE == 0 || c.mc_params) && c.world > 1;
+    const int env_blocks = comm_blocks(MODE, c.world, nvls);
     bool oneshot;
     if (algo == 1) oneshot = true;
     else if (algo == 2) oneshot = false;
@@ -365,7 +385,6 @@ static int launch_allreduce(int64_t off, int64_t n, float *m, float scale, float
     // small messages: only as many blocks as there is data (same on every rank: a function of n)
     int blocks = env_blocks;            // two-shot kernels stride over their slice, so any grid <= kCommBlocks works (same on every rank)
     if (oneshot) { int64_t need = (n4 + threads - 1) / threads; if (need < blocks) blocks = need < 1 ? 1 : (int)need; }
-    const bool nvls = c.use_nvls && c.mc_grads && (MODE == 0 || c.mc_params) && c.world > 1;
 #define LAUNCH_W(Wv)                                                                                              \
     if (nvls && oneshot) { B2_LAUNCH((k_allreduce_nvls<Wv, MODE, true>), blocks, threads, 0, s, c.ptrs, c.rank, c.mc_grads, c.mc_params, m, \
                                      off, n4, scale, lr, momentum, first, mirror, c.epoch, c.err); }                  \
@@ -509,9 +528,9 @@ int b2_comm_barrier(void *stream) {
     B2_CHECK(c.inited && c.registered, B2_ERR_STATE, "comm: not initialised / no buffers registered");
     switch (c.world) {
     case 1: return 0;
-    case 2: B2_LAUNCH((k_barrier_only<2>), comm_blocks(), comm_threads(), 0, stream, c.ptrs, c.rank, c.epoch, c.err); break;
-    case 4: B2_LAUNCH((k_barrier_only<4>), comm_blocks(), comm_threads(), 0, stream, c.ptrs, c.rank, c.epoch, c.err); break;
-    case 8: B2_LAUNCH((k_barrier_only<8>), comm_blocks(), comm_threads(), 0, stream, c.ptrs, c.rank, c.epoch, c.err); break;
+    case 2: B2_LAUNCH((k_barrier_only<2>), comm_blocks(0, c.world, false), comm_threads(), 0, stream, c.ptrs, c.rank, c.epoch, c.err); break;
+    case 4: B2_LAUNCH((k_barrier_only<4>), comm_blocks(0, c.world, false), comm_threads(), 0, stream, c.ptrs, c.rank, c.epoch, c.err); break;
+    case 8: B2_LAUNCH((k_barrier_only<8>), comm_blocks(0, c.world, false), comm_threads(), 0, stream, c.ptrs, c.rank, c.epoch, c.err); break;
     default: set_error("comm: world size %d not supported", c.world); return B2_ERR_UNSUPPORTED;
     }
     return 0;

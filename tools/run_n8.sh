@@ -11,8 +11,8 @@ except Exception as e: print("$2 parse", e)
 PY
 }
 timeout 600 $TR --master-port 29555 bench.py --gpus $W --steps 20 --warmup 5 > gpurun_out/r02_bench_n$W.json 2> gpurun_out/bench_n$W.err; tail -2 gpurun_out/bench_n$W.err; show gpurun_out/r02_bench_n$W.json "N=$W default"
-for th in 256 128; do
-B2_COMM_THREADS=$th timeout 300 $TR --master-port 29577 bench.py --gpus $W --steps 20 --warmup 5 --no-secondary --no-parity --no-cpu-baseline > gpurun_out/r02_bench_n${W}_t$th.json 2> gpurun_out/sw.err; show gpurun_out/r02_bench_n${W}_t$th.json "N=$W nvls t$th"
+for cfg in "48 512" "32 512" "24 512" "48 256" "64 512"; do
+set -- $cfg
+B2_COMM_BLOCKS=$1 B2_COMM_THREADS=$2 timeout 300 $TR --master-port 29577 bench.py --gpus $W --steps 20 --warmup 5 --no-secondary --no-parity --no-cpu-baseline > gpurun_out/r02_bench_n${W}_cb$1_t$2.json 2> gpurun_out/sw.err; show gpurun_out/r02_bench_n${W}_cb$1_t$2.json "N=$W nvls cb$1 t$2"
 done
-B2_COMM_BLOCKS=48 timeout 300 $TR --master-port 29578 bench.py --gpus $W --steps 20 --warmup 5 --no-secondary --no-parity --no-cpu-baseline > gpurun_out/r02_bench_n${W}_cb48.json 2> gpurun_out/sw.err; show gpurun_out/r02_bench_n${W}_cb48.json "N=$W nvls cb48"
-B2_NVLS=0 timeout 300 $TR --master-port 29579 bench.py --gpus $W --steps 20 --warmup 5 --no-secondary --no-parity --no-cpu-baseline > gpurun_out/r02_bench_n${W}_p2p.json 2> gpurun_out/sw.err; show gpurun_out/r02_bench_n${W}_p2p.json "N=$W p2p"
+B2_NVLS=0 B2_COMM_BLOCKS=48 timeout 300 $TR --master-port 29579 bench.py --gpus $W --steps 20 --warmup 5 --no-secondary --no-parity --no-cpu-baseline > gpurun_out/r02_bench_n${W}_p2p_cb48.json 2> gpurun_out/sw.err; show gpurun_out/r02_bench_n${W}_p2p_cb48.json "N=$W p2p cb48"
