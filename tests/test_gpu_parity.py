@@ -398,3 +398,44 @@ def test_ce_kernel_against_c_oracle_fp64():
     torch.cuda.synchronize()
     assert abs(float(loss) - ref_loss.value) < 2e-6
     np.testing.assert_allclose(d.cpu().numpy(), ref_d, rtol=2e-5, atol=2e-9)
+
+
+@pytest.mark.gpu
+def test_kernel_trace_records_one_step():
+    """b2_trace_start / b2_trace_stop (include/b2ddp.h): every kernel of a training step -- also inside the replayed
+    CUDA graphs -- leaves a (tag, %globaltimer) record; tags decode to source lines of __global__ functions."""
+    import ctypes as C
+    torch.manual_seed(0)
+    net = b2.Net().to(DEV)
+    crit = b2.CrossEntropyLoss()
+    opt = b2.SGD(net.parameters(), lr=0.001, momentum=0.9)
+    x = torch.randn(4, 3, 32, 32).to(DEV)
+    y = torch.randint(0, 10, (4,)).to(DEV)
+
+    def step():
+        opt.zero_grad()
+        loss = crit(net(x), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(6):                       # past the eager warm-up: forward/backward replay from graphs
+        step()
+    torch.cuda.synchronize()
+    launches0 = b2.lib().b2_launch_count()
+    b2._lib.call("b2_trace_start", 1024)
+    step()
+    torch.cuda.synchronize()
+    launches = b2.lib().b2_launch_count() - launches0
+    rec = (C.c_ulonglong * 2048)()
+    n = C.c_int(0)
+    b2._lib.call("b2_trace_stop", rec, 1024, C.byref(n))
+    begins = [(rec[2 * i], rec[2 * i + 1]) for i in range(n.value) if (rec[2 * i] & 15) == 0]
+    assert launches > 10 and abs(len(begins) - launches) <= 2, (len(begins), launches)     # one "begin" per launched kernel
+    assert all(1 <= (tag >> 24) <= 4 and ((tag >> 4) & 0xFFFFF) > 0 for tag, _ in begins)
+    ts = sorted(t for _, t in begins)
+    assert 0 < ts[-1] - ts[0] < 50_000_000                            # one small step: well under 50 ms of %globaltimer
+    # switched off again: a further step records nothing and a second stop is an error
+    step(); torch.cuda.synchronize()
+    with pytest.raises(b2.B2Error):
+        b2._lib.call("b2_trace_stop", rec, 1024, C.byref(n))
