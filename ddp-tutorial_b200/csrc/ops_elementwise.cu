@@ -540,6 +540,30 @@ k_maxpool_fwd_bf16x8(const bf16 *__restrict__ x, bf16 *__restrict__ y, uint8_t *
         float best[8]; int bi[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bi[e] = 255; }
+        if (KK) {
+            // compile-time window: all KK*KK (predicated) loads first, then the compare chain in the same order
+            constexpr int KW = KK ? KK : 1;
+            uint4 raw[KW * KW]; bool ok[KW * KW];
+#pragma unroll
+            for (int a = 0; a < KW; ++a)
+#pragma unroll
+                for (int b = 0; b < KW; ++b) {
+                    const int hi = oh * SS - PP + a, wi = ow * SS - PP + b;
+                    ok[a * KW + b] = hi >= 0 && hi < Hi && wi >= 0 && wi < Wi;
+                    raw[a * KW + b] = make_uint4(0u, 0u, 0u, 0u);
+                    if (ok[a * KW + b]) raw[a * KW + b] = *(const uint4 *)(x + (((int64_t)n * Hi + hi) * Wi + wi) * C + c8 * 8);
+                }
+#pragma unroll
+            for (int j = 0; j < KW * KW; ++j) {
+                if (!ok[j]) continue;
+                const bf16 *v = (const bf16 *)&raw[j];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float f = __bfloat162float(v[e]);
+                    if (f > best[e] || bi[e] == 255) { best[e] = f; bi[e] = j; }
+                }
+            }
+        } else
         for (int a = 0; a < k; ++a) {
             int hi = oh * stride - pad + a;
             if (hi < 0 || hi >= Hi) continue;
@@ -586,6 +610,34 @@ k_maxpool_bwd_bf16x8(const bf16 *__restrict__ dy, const uint8_t *__restrict__ id
         float g[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) g[e] = 0.f;
+        if (KK == 3 && SS == 2 && PP == 1) {
+            // 3x3 / stride 2 / pad 1: pixel (hi, wi) lies in window row hi>>1 (at row (hi&1)+1 of it) and, for odd hi,
+            // also in window row (hi>>1)+1 (at its row 0); same for columns.  All (up to) four candidate windows are
+            // loaded at once instead of one dependent round trip per window.
+            const int ohA = hi >> 1, owA = wi >> 1;
+            const bool rowA = ohA < Ho, colA = owA < Wo;
+            const bool rowB = (hi & 1) && (ohA + 1 < Ho), colB = (wi & 1) && (owA + 1 < Wo);
+            const int rA = (hi & 1) + 1, cA = (wi & 1) + 1;
+            const bool ok[4] = {rowA && colA, rowA && colB, rowB && colA, rowB && colB};
+            const int code[4] = {rA * 3 + cA, rA * 3, cA, 0};
+            uint2 iraw[4]; uint4 draw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                iraw[j] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);          // 255 never equals a window position (0..8)
+                draw[j] = make_uint4(0u, 0u, 0u, 0u);
+                if (ok[j]) {
+                    const int64_t o = ((((int64_t)n * Ho + (ohA + (j >> 1))) * Wo + (owA + (j & 1))) * C8 + c8) * 8;
+                    iraw[j] = *(const uint2 *)(idx + o);
+                    draw[j] = *(const uint4 *)(dy + o);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint8_t *ix = (const uint8_t *)&iraw[j]; const bf16 *dv = (const bf16 *)&draw[j];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (ix[e] == code[j]) g[e] += __bfloat162float(dv[e]);
+            }
+        } else {
         int oh_lo = hi + pad - k + stride; oh_lo = oh_lo < 0 ? 0 : oh_lo / stride;
         int oh_hi = (hi + pad) / stride; if (oh_hi > Ho - 1) oh_hi = Ho - 1;
         int ow_lo = wi + pad - k + stride; ow_lo = ow_lo < 0 ? 0 : ow_lo / stride;
@@ -600,6 +652,7 @@ k_maxpool_bwd_bf16x8(const bf16 *__restrict__ dy, const uint8_t *__restrict__ id
 #pragma unroll
                 for (int e = 0; e < 8; ++e) if (ix[e] == mine) g[e] += __bfloat162float(dv[e]);
             }
+        }
         __align__(16) bf16 o8[8];
         if (acc) {
             uint4 old = *(const uint4 *)(dx + i * 8);
