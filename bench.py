@@ -131,10 +131,13 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{MODEL}(num_classes=10) train step, batch {BATCH}, 3x32x32 synthetic, SGD(0.001,0.9)",
+        # same workload naming as this repo's arm (run_b2); the CPU times a bounded sample of it: one batch of BATCH per step
+        "config": {"workload": f"{MODEL}(num_classes=10) training step, per-GPU batch {BATCH}, 3x32x32 synthetic "
+                               f"(BASELINE configs[{(1 if args.gpus == 1 else 2) if MODEL == 'resnet18' else 3}])",
+                   "global_batch": args.gpus * BATCH, "parallelism": f"dp{args.gpus}", "precision": "fp32",
                    "where": "host CPU cores, torch CPU kernels (the reference's own code path: cifar_example.py:66-87)"},
         "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps of batch {BATCH} after {args.warmup} warm-up"},
+                         "sample": f"{args.steps} steps of one batch of {BATCH} (rank 0's shard of the global batch) after {args.warmup} warm-up"},
         "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
