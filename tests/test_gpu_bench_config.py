@@ -372,3 +372,47 @@ def test_dropin_script_runs_and_prints_the_reference_lines(tmp_path):
         assert abs(got - want) < 2e-3, (line, want)
     sd = torch.load(tmp_path / "cifar_net.pth", map_location="cpu")
     assert list(sd) == [n for n, _ in O.NET_PARAM_SHAPES]
+
+
+def _fake_cifar(root, n_train_per_file=24, n_test=40, seed=3):
+    """cifar-10-batches-py in the python-pickle layout torchvision.datasets.CIFAR10 reads (cifar_example_ddp.py:67-68)."""
+    import pickle
+    rng = np.random.default_rng(seed)
+    base = os.path.join(root, "cifar-10-batches-py")
+    os.makedirs(base)
+    out = {}
+    for name, n in [(f"data_batch_{i}", n_train_per_file) for i in range(1, 6)] + [("test_batch", n_test)]:
+        d = {"data": rng.integers(0, 256, size=(n, 3072), dtype=np.uint8), "labels": [int(v) for v in rng.integers(0, 10, size=n)]}
+        with open(os.path.join(base, name), "wb") as f:
+            pickle.dump(d, f)
+        out[name] = d
+    return out
+
+
+def test_dropin_script_real_data_branch_eval_loop_and_checkpoint(tmp_path):
+    """The branch of the drop-in script a user with the dataset takes (cifar_example_ddp.py:67-71 loaders, :90-114
+    epoch loop with sampler.set_epoch, :118-119 checkpoint, :121-136 accuracy loop), on a small fake
+    cifar-10-batches-py: uint8 images resident in HBM, normalised on the device, DistributedSampler order."""
+    import subprocess
+    import sys
+    files = _fake_cifar(str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "ddp-tutorial_b200", "cifar_example_ddp.py"), "--model", "net", "--batch-size", "4",
+                        "--epochs", "2", "--print-every", "10", "--data", str(tmp_path), "--save", str(tmp_path / "cifar_net.pth")],
+                       capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = r.stdout
+    assert "Finished Training" in out
+    # 120 training images / batch 4 = 30 steps per epoch -> 3 print lines per epoch, 2 epochs
+    assert len([l for l in out.splitlines() if l.startswith("[1,")]) == 3 and len([l for l in out.splitlines() if l.startswith("[2,")]) == 3, out
+    acc_lines = [l for l in out.splitlines() if l.startswith("Accuracy of the network on the 10000 test images:")]
+    assert len(acc_lines) == 1, out
+    acc = int(acc_lines[0].split(":")[1].strip().rstrip("%").strip())
+    assert 0 <= acc <= 100
+    # the saved state_dict loads into the reference's module and reproduces the printed accuracy on the same test file
+    sd = torch.load(tmp_path / "cifar_net.pth", map_location="cpu")
+    assert list(sd) == [n for n, _ in O.NET_PARAM_SHAPES]
+    x = torch.from_numpy(files["test_batch"]["data"].reshape(-1, 3, 32, 32)).float().div(255.0).sub(0.5).div(0.5)   # ToTensor + Normalize(.5,.5)
+    y = torch.tensor(files["test_batch"]["labels"])
+    with torch.no_grad():
+        ref_acc = (O.net_forward({k: v.float() for k, v in sd.items()}, x).argmax(1) == y).float().mean().item()   # the reference's Net.forward
+    assert abs(ref_acc * 100 - acc) <= 100.0 / len(y) + 1.0, (ref_acc, acc)        # printed with %d (truncation) + one borderline sample
