@@ -227,3 +227,24 @@ def test_op_schedule_and_kernel_selection():
         assert fused == (20 if prec == "bf16" else 0)
         assert b2.lib().b2_model_workspace_bytes(h) > 0
         b2.lib().b2_model_destroy(h)
+
+
+def test_committed_launch_list_reproduces_the_traffic_figure(tmp_path):
+    """profiles/r02_traffic.json (what bench.py copies into roofline.traffic) is derived from the committed ncu launch
+    list by tools/traffic_summary.py: re-derive it and compare, and check the step it describes is a whole step."""
+    import json
+    import subprocess
+    import sys
+    out = tmp_path / "traffic.json"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "traffic_summary.py"),
+                        os.path.join(ROOT, "profiles", "r02_launches_dram.csv"), str(out)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    got = json.load(open(out))
+    want = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    assert got["step_launches"] == want["step_launches"] == 93
+    assert got["conv_launches_per_step"] == 39                         # 20 fprop (incl. the stem) + 19 dgrad
+    assert abs(got["conv_dram_bytes_per_launch"] - want["conv_dram_bytes_per_launch"]) < 1.0
+    k = got["per_kernel"]
+    assert k["void k_wgrad<0>"]["n"] + k["void k_wgrad<1>"]["n"] == 20 and k["k_sgd"]["n"] == 3
+    # activations live in L2: the whole step moves well under 1 GB through DRAM
+    assert 0.3e9 < got["step_dram_read_bytes"] + got["step_dram_write_bytes"] < 1.0e9
